@@ -1,0 +1,154 @@
+"""Synthetic Go2 MPC records (the inputs of one ``solve_QP`` call per robot), batched.
+
+The reference produces these per cycle in ``com_trajectory.py:37-211`` from Pinocchio/MuJoCo state,
+neither of which exists here, so the workload is generated: SURVEY.md section 8(d) configs #1-#5.  A record
+is the *raw* input of the hot path (what ``ComTraj`` holds before ``_continuousDynamics``):
+
+    x0      (B, 12)        [p, rpy, v, omega] world frame         com_trajectory.py:37
+    x_ref   (B, 12, N)     rows [p; rpy; v; omega], col i <-> (i+1) dt   com_trajectory.py:15-25,84-103
+    r_foot  (B, 4, 3, N)   lever arms CoM->foot, world, legs FL FR RL RR  com_trajectory.py:204-207
+    I_world (B, 3, 3)      centroidal inertia in world frame      com_trajectory.py:40
+    mass    (B,)                                                  com_trajectory.py:39
+    t0      (B,)           time_now fed to the gait schedule      com_trajectory.py:106
+    dt, gait_hz, duty      scalars                                test_MPC.py:50-52,67
+
+Host-side NumPy only: generating synthetic inputs is not part of the hot path.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+GO2_MASS = 15.02                      # placeholder Go2 values (URDF not in the reference tree)
+GO2_I_BODY = np.array([0.11, 0.33, 0.38])
+HIP_X, HIP_Y = 0.1934, 0.142
+PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])   # gait.py:8
+
+
+@dataclass
+class Records:
+    x0: np.ndarray
+    x_ref: np.ndarray
+    r_foot: np.ndarray
+    I_world: np.ndarray
+    mass: np.ndarray
+    t0: np.ndarray
+    dt: float
+    gait_hz: float
+    duty: float
+    N: int
+
+    @property
+    def B(self):
+        return self.x0.shape[0]
+
+    def slice(self, lo, hi):
+        return Records(self.x0[lo:hi], self.x_ref[lo:hi], self.r_foot[lo:hi], self.I_world[lo:hi],
+                       self.mass[lo:hi], self.t0[lo:hi], self.dt, self.gait_hz, self.duty, self.N)
+
+    def shard(self, rank, world):
+        """Contiguous slice of ceil(B/world) robots for ``rank``."""
+        per = -(-self.B // world)
+        return self.slice(min(rank * per, self.B), min((rank + 1) * per, self.B))
+
+
+def _rot_zyx(roll, pitch, yaw):
+    cr, sr = np.cos(roll), np.sin(roll)
+    cp, sp = np.cos(pitch), np.sin(pitch)
+    cy, sy = np.cos(yaw), np.sin(yaw)
+    R = np.empty(roll.shape + (3, 3))
+    R[..., 0, 0] = cy * cp
+    R[..., 0, 1] = cy * sp * sr - sy * cr
+    R[..., 0, 2] = cy * sp * cr + sy * sr
+    R[..., 1, 0] = sy * cp
+    R[..., 1, 1] = sy * sp * sr + cy * cr
+    R[..., 1, 2] = sy * sp * cr - cy * sr
+    R[..., 2, 0] = -sp
+    R[..., 2, 1] = cp * sr
+    R[..., 2, 2] = cp * cr
+    return R
+
+
+def host_contact_table(t0, dt, N, gait_hz, duty, phase_offset=PHASE_OFFSET):
+    """Batched stance table (B, 4, N) int32 with the reference's arithmetic order (gait.py:26-37).
+    Host twin of the device kernel ``cmpc_contact_table``; used to lay out synthetic lever arms."""
+    t0 = np.asarray(t0, dtype=np.float64).reshape(-1)
+    T = 1 / gait_hz
+    t = t0[:, None] + np.arange(N)[None, :] * dt
+    t = t + dt / 2
+    ph = np.mod(np.asarray(phase_offset)[None, :, None] + t[:, None, :] / T, 1.0)
+    return (ph < duty).astype(np.int32)
+
+
+def random_records(B, N=16, seed=None, gait_hz=3.0, duty=0.6, stress=0.0):
+    """Config #3/#5 generator: i.i.d. Go2 trot states and references.
+
+    ``stress`` in [0,1] mixes in large velocity/attitude disturbances (lateral shoves, falls) so
+    that friction-pyramid and fz_min constraints become active.
+    """
+    rng = np.random.default_rng(B if seed is None else seed)
+    dt = (1.0 / gait_hz) / N
+    t0 = 1e-3 * rng.integers(0, 10000, size=B).astype(np.float64)
+    yaw = rng.uniform(-np.pi, np.pi, B)
+    roll = np.clip(rng.normal(0, 0.05, B), -0.15, 0.15)
+    pitch = np.clip(rng.normal(0, 0.05, B), -0.15, 0.15)
+    cmd = np.stack([rng.uniform(-0.8, 0.8, B), rng.uniform(-0.4, 0.4, B), np.zeros(B)], axis=1)
+    wz = rng.uniform(-4.0, 4.0, B)
+    p = np.stack([rng.uniform(-5, 5, B), rng.uniform(-5, 5, B), 0.27 + rng.normal(0, 0.01, B)], axis=1)
+    cy, sy = np.cos(yaw), np.sin(yaw)
+    v_des = np.stack([cy * cmd[:, 0] - sy * cmd[:, 1], sy * cmd[:, 0] + cy * cmd[:, 1], np.zeros(B)], axis=1)
+    v = v_des + rng.normal(0, 0.1, (B, 3))
+    om = np.stack([rng.normal(0, 0.2, B), rng.normal(0, 0.2, B), wz + rng.normal(0, 0.2, B)], axis=1)
+    if stress > 0:
+        hit = rng.random(B) < stress
+        v = v + hit[:, None] * rng.normal(0, 1.0, (B, 3))
+        roll = roll + hit * rng.normal(0, 0.2, B)
+        pitch = pitch + hit * rng.normal(0, 0.2, B)
+    x0 = np.concatenate([p, np.stack([roll, pitch, yaw], axis=1), v, om], axis=1)
+
+    # reference trajectory: com_trajectory.py:47-103 (position target within +-0.1 m of the state)
+    pos_des = p.copy()
+    pos_des[:, :2] += rng.uniform(-0.1, 0.1, (B, 2))
+    pos_des[:, 2] = 0.27
+    tv = (np.arange(N) + 1) * dt
+    x_ref = np.zeros((B, 12, N))
+    x_ref[:, 0:3, :] = pos_des[:, :, None] + v_des[:, :, None] * tv[None, None, :]
+    x_ref[:, 5, :] = yaw[:, None] + wz[:, None] * tv[None, :]
+    x_ref[:, 6:9, :] = v_des[:, :, None]
+    x_ref[:, 11, :] = wz[:, None]
+
+    # inertia: body diag rotated into the world frame
+    R = _rot_zyx(roll, pitch, yaw)
+    I_world = np.einsum("bij,j,bkj->bik", R, GO2_I_BODY, R)
+    mass = np.full(B, GO2_MASS)
+
+    # lever arms: nominal hip position under the body, constant within a stance segment, 0 in swing
+    table = host_contact_table(t0, dt, N, gait_hz, duty)                    # (B,4,N)
+    hips = np.array([[HIP_X, HIP_Y], [HIP_X, -HIP_Y], [-HIP_X, HIP_Y], [-HIP_X, -HIP_Y]])
+    r_foot = np.zeros((B, 4, 3, N))
+    # segment id per (b, leg, k): increments at every swing->stance edge
+    edge = np.zeros((B, 4, N), dtype=np.int64)
+    edge[:, :, 1:] = (table[:, :, 1:] == 1) & (table[:, :, :-1] == 0)
+    seg = np.cumsum(edge, axis=2)                                           # 0..2
+    noise = rng.normal(0, 0.03, (B, 4, 3, 2))                               # per segment xy jitter
+    for leg in range(4):
+        hx = cy * hips[leg, 0] - sy * hips[leg, 1]
+        hy = sy * hips[leg, 0] + cy * hips[leg, 1]
+        jit = np.take_along_axis(noise[:, leg], np.minimum(seg[:, leg], 2)[:, :, None], axis=1)  # (B,N,2)
+        st = table[:, leg, :].astype(np.float64)
+        r_foot[:, leg, 0, :] = (hx[:, None] + jit[:, :, 0]) * st
+        r_foot[:, leg, 1, :] = (hy[:, None] + jit[:, :, 1]) * st
+        r_foot[:, leg, 2, :] = (-p[:, 2])[:, None] * st
+    return Records(x0, x_ref, r_foot, I_world, mass, t0, dt, gait_hz, duty, N)
+
+
+def srb_closed_loop_step(rec, Ad, Bd, gd, u0, mpc_period=0.02, rng=None, noise=0.0):
+    """Advance every robot by one MPC period with the first-step forces (stand-in for MuJoCo,
+    SURVEY.md section 8f-2): x+ = x + (mpc_period/dt) * (Ad x + Bd[0] u0 + gd - x), then rebuild the
+    reference window from the new state.  Used to make warm-start sequences (configs #1/#2)."""
+    frac = mpc_period / rec.dt
+    x = rec.x0
+    xn = np.einsum("bij,bj->bi", Ad, x) + np.einsum("bij,bj->bi", Bd[:, 0], u0) + gd.reshape(-1, 12)
+    x_new = x + frac * (xn - x)
+    if noise and rng is not None:
+        x_new = x_new + rng.normal(0, noise, x_new.shape)
+    return x_new
