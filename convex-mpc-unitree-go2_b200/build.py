@@ -1,0 +1,49 @@
+"""Compile the CUDA library in-tree for sm_100a (B200).  No JIT cache, no torch extension machinery:
+one nvcc command, the resulting ``libcmpc.so`` sits next to this file and travels with the repo."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "cmpc.cu")
+DEPS = [SRC, os.path.join(HERE, "csrc", "cmpc_core.cuh"),
+        os.path.join(os.path.dirname(HERE), "include", "cmpc.h")]
+LIB = os.path.join(HERE, "libcmpc.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def find_nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA toolkit is required to build libcmpc.so")
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    """Build ``libcmpc.so`` if missing or older than its sources.  Returns the path."""
+    if not force and not is_stale():
+        return LIB
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(" ".join(cmd))
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libcmpc.so")
+    with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:
+        f.write(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,398 @@
+"""Batched, B200-native drop-in for ``convex_mpc/centroidal_mpc.py`` of the reference.
+
+Same constructor, same per-cycle ``solve_QP(go2, traj, verbose)`` call, same module constants and
+the same ``sol["x"]`` layout ``w = [x_1..x_N ; u_0..u_{N-1}]`` (centroidal_mpc.py:44,
+test_MPC.py:189-192) -- but every ``traj`` field may carry a leading batch dimension of independent
+robots, and the QP is built and solved on the GPU by ``libcmpc.so`` (csrc/cmpc.cu) through the C-ABI
+of ``include/cmpc.h``.  PyTorch tensors are used as device buffers only.
+
+There is no CPU fallback: importing this module without ``libcmpc.so`` raises.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+# --------------------------------------------------------------------------------
+# Model Predictive Control Setting  (same names and values as centroidal_mpc.py:12-38)
+# --------------------------------------------------------------------------------
+COST_MATRIX_Q = np.diag([1, 1, 50, 10, 20, 1, 2, 2, 1, 1, 1, 1])
+COST_MATRIX_R = np.diag([1e-5] * 12)
+
+MU = 0.8
+NX = 12
+NU = 12
+FZ_MIN = 10      # centroidal_mpc.py:127 (hard-coded inside _compute_bounds in the reference)
+
+OPTS = {
+    'warm_start_primal': True,
+    'warm_start_dual': True,
+
+    "osqp": {
+        "eps_abs": 1e-4,
+        "eps_rel": 1e-4,
+        "max_iter": 1000,
+        "polish": False,
+        "verbose": False,
+        'adaptive_rho': True,
+        "check_termination": 10,
+        'adaptive_rho_interval': 25,
+        "scaling": 5,
+        "scaled_termination": True
+    }
+}
+
+SOLVER_NAME: str = "osqp"        # the reference's CasADi plugin name, kept for importers
+BACKEND: str = "cmpc-b200"       # what actually runs here
+
+PHASE_OFFSET = (0.5, 0.0, 0.0, 0.5)   # gait.py:8
+
+_LEG_FIELDS = ("r_fl_foot_world", "r_fr_foot_world", "r_rl_foot_world", "r_rr_foot_world")
+
+
+class _DM:
+    """Tiny stand-in for ``casadi.DM`` so that ``sol["x"].full().flatten()`` (test_MPC.py:190) works."""
+
+    def __init__(self, tensor, batched):
+        self.tensor = tensor
+        self._batched = batched
+
+    def full(self):
+        a = self.tensor.detach().cpu().numpy()
+        return a if self._batched else a.reshape(-1, 1)
+
+    def __array__(self, dtype=None):
+        a = self.full()
+        return a.astype(dtype) if dtype is not None else a
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape) if self._batched else (self.tensor.numel(), 1)
+
+
+class MPCSolution(dict):
+    """Result of one ``solve_QP``.  Keys of the CasADi dict the reference uses (``x``, ``lam_x``,
+    ``lam_a``, ``cost``) plus batched extras (``u`` (B,12,N), ``X`` (B,12,N), ``status``, ``iters``,
+    ``r_prim``, ``r_dual``, ``stats``).  Tensors stay on the device until asked for."""
+
+
+class BatchedComTraj:
+    """Duck-typed stand-in for the reference's ``ComTraj`` with a leading batch dimension.
+
+    Carries exactly the members ``solve_QP`` reads under the reference's names:
+    ``N, initial_x_vec, compute_x_ref_vec(), contact_table`` and either ``Ad, Bd, gd`` or the raw
+    fields ``m, I_com_world, r_*_foot_world`` from which the GPU computes them
+    (com_trajectory.py:221-286).  ``time_now`` + ``gait_hz``/``gait_duty`` let the GPU compute the
+    contact table as well (gait.py:26-37).
+    """
+
+    def __init__(self, N, initial_x_vec, x_ref, dt, *, Ad=None, Bd=None, gd=None, m=None, I_com_world=None,
+                 r_foot=None, contact_table=None, time_now=None, gait_hz=3.0, gait_duty=0.6,
+                 phase_offset=PHASE_OFFSET):
+        self.N = int(N)
+        self.initial_x_vec = initial_x_vec
+        self._x_ref = x_ref
+        self.dt = float(dt)
+        self.Ad, self.Bd, self.gd = Ad, Bd, gd
+        self.m, self.I_com_world = m, I_com_world
+        self.r_foot = r_foot
+        if r_foot is not None:
+            for i, name in enumerate(_LEG_FIELDS):
+                setattr(self, name, r_foot[..., i, :, :])
+        self.contact_table = contact_table
+        self.time_now = time_now
+        self.gait_hz, self.gait_duty, self.phase_offset = gait_hz, gait_duty, tuple(phase_offset)
+
+    def compute_x_ref_vec(self):
+        return self._x_ref
+
+    @classmethod
+    def from_records(cls, rec, device=None, with_contact_table=False):
+        """Wrap a ``records.Records`` batch; ``device`` moves the arrays to that CUDA device."""
+        def mv(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(device) if device is not None else t
+        ct = None
+        if with_contact_table:
+            from .records import host_contact_table
+            ct = mv(host_contact_table(rec.t0, rec.dt, rec.N, rec.gait_hz, rec.duty))
+        return cls(rec.N, mv(rec.x0), mv(rec.x_ref), rec.dt, m=mv(rec.mass), I_com_world=mv(rec.I_world),
+                   r_foot=mv(rec.r_foot), contact_table=ct, time_now=mv(rec.t0), gait_hz=rec.gait_hz,
+                   gait_duty=rec.duty)
+
+
+class CentroidalMPC:
+    """Batched convex MPC.  ``CentroidalMPC(go2, traj)`` then ``solve_QP(go2, traj)`` per cycle.
+
+    ``go2`` is unused, exactly as in the reference (centroidal_mpc.py:41,69).
+
+    Extra keyword arguments (all optional, defaults follow the reference ``OPTS``):
+      device      CUDA device (default: current)
+      mode        "active_set" (default): exact active-set solve with ADMM fallback;
+                  "admm": OSQP-equivalent ADMM only, terminated by eps_abs/eps_rel
+      dynamics    "auto" (default): use ``traj.Ad/Bd/gd`` when present, else compute them on the GPU
+                  from ``traj.m, I_com_world, r_*_foot_world``; "traj" / "device" force one
+      eps_abs, eps_rel, max_iter, polish, check_termination, adaptive_rho_interval, rho0, sigma, alpha
+      max_stance  upper bound on stance foot-steps per robot (see cmpc_set_max_stance)
+    """
+
+    def __init__(self, go2, traj, *, device=None, mode="active_set", dynamics="auto", max_batch=None,
+                 eps_abs=None, eps_rel=None, max_iter=None, polish=None, check_termination=None,
+                 adaptive_rho_interval=None, rho0=1e-4, sigma=1e-6, alpha=1.6, mu=MU, fz_min=FZ_MIN,
+                 Q=None, R=None, max_stance=None, verbose=True):
+        if not torch.cuda.is_available():
+            raise _lib.CmpcError("CentroidalMPC needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.Q = COST_MATRIX_Q if Q is None else np.asarray(Q, dtype=float)
+        self.R = COST_MATRIX_R if R is None else np.asarray(R, dtype=float)
+        self.N = int(traj.N)
+        self.nvars = self.N * NX + self.N * NU          # centroidal_mpc.py:44
+        self.solve_time = 0.0
+        self.update_time = 0.0
+        self.mode = mode
+        self.dynamics = dynamics
+        o = OPTS["osqp"]
+        self.opts = dict(
+            eps_abs=o["eps_abs"] if eps_abs is None else eps_abs,
+            eps_rel=o["eps_rel"] if eps_rel is None else eps_rel,
+            max_iter=o["max_iter"] if max_iter is None else max_iter,
+            polish=o["polish"] if polish is None else polish,
+            check_termination=o["check_termination"] if check_termination is None else check_termination,
+            adaptive_rho_interval=(o["adaptive_rho_interval"] if o["adaptive_rho"] else 0)
+            if adaptive_rho_interval is None else adaptive_rho_interval,
+            rho0=rho0, sigma=sigma, alpha=alpha, mu=mu, fz_min=fz_min)
+        B = self._batch_of(traj)
+        self.max_batch = int(max_batch if max_batch is not None else max(B, 1))
+        h = ctypes.c_void_p()
+        check(self._lib.cmpc_create(self.N, self.max_batch, self.device.index or 0, ctypes.byref(h)))
+        self._h = h
+        self._push_params()
+        if max_stance is not None:
+            check(self._lib.cmpc_set_max_stance(self._h, int(max_stance)))
+        self._state_B = None
+        self._warm = False
+        self.x_prev = self.lam_x_prev = self.lam_a_prev = None
+        self.last_stats = None
+        if verbose:
+            n, N = self.nvars, self.N
+            print("\n[QP Init] ===== MPC QP Structure =====")
+            print(f"  reference form: vars {n} | constr {28 * N} | horizon N = {N}")
+            print(f"  condensed form: vars {12 * N} (stance only) | rows 5 per stance foot-step | backend {BACKEND}")
+            print("[QP Init] ✓ Initialization complete.\n")
+
+    # ------------------------------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.cmpc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _push_params(self):
+        o = self.opts
+        Q = _lib.darr(np.diag(self.Q) if np.ndim(self.Q) == 2 else self.Q)
+        R = _lib.darr(np.diag(self.R) if np.ndim(self.R) == 2 else self.R)
+        mode = {"admm": _lib.MODE_ADMM, "active_set": _lib.MODE_ACTIVE_SET}[self.mode]
+        check(self._lib.cmpc_set_params(self._h, Q, R, o["mu"], o["fz_min"], o["eps_abs"], o["eps_rel"],
+                                        int(o["max_iter"]), o["rho0"], o["sigma"], o["alpha"], mode,
+                                        int(bool(o["polish"])), int(o["check_termination"]),
+                                        int(o["adaptive_rho_interval"])))
+
+    def set_max_stance(self, nfmax):
+        check(self._lib.cmpc_set_max_stance(self._h, int(nfmax)))
+
+    def reset(self):
+        """Forget the warm-start state (the reference has no such call: it warm-starts forever)."""
+        self._warm = False
+        self.x_prev = self.lam_x_prev = self.lam_a_prev = None
+
+    # ------------------------------------------------------------------------------------------
+    def _batch_of(self, traj):
+        x0 = traj.initial_x_vec
+        shp = tuple(x0.shape)
+        if len(shp) == 1 or (len(shp) == 2 and shp == (12, 1)):
+            return 0       # un-batched (reference shapes)
+        return int(shp[0])
+
+    def _dev(self, a, shape):
+        """Device FP64 contiguous tensor of ``shape`` from numpy / torch input (no copy if possible)."""
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.reshape(shape).contiguous()
+
+    def _alloc_state(self, B):
+        if self._state_B == B:
+            return
+        N, dev = self.N, self.device
+        if B > self.max_batch:
+            raise _lib.CmpcError(f"batch {B} exceeds max_batch {self.max_batch} given at construction")
+        f64 = dict(dtype=torch.float64, device=dev)
+        self._u = torch.zeros(B, 12 * N, **f64)
+        self._y = torch.zeros(B, 28 * N, **f64)
+        self._rho = torch.zeros(B, **f64)
+        self._X = torch.empty(B, 12 * N, **f64)
+        self._nu = torch.empty(B, 12 * N, **f64)
+        self._stats = torch.empty(B, _lib.NSTAT, **f64)
+        self._status = torch.empty(B, dtype=torch.int32, device=dev)
+        self._iters = torch.empty(B, dtype=torch.int32, device=dev)
+        self._mask = torch.empty(B, (4 * N + 63) // 64, dtype=torch.int64, device=dev)
+        self._state_B = B
+        self._warm = False
+
+    def _gather(self, traj, B, stream):
+        """Collect device pointers for one call.  Returns (dict of tensors kept alive, use_AdBd)."""
+        N = self.N
+        t = {}
+        t["x0"] = self._dev(traj.initial_x_vec, (B, 12))
+        t["x_ref"] = self._dev(traj.compute_x_ref_vec(), (B, 12, N))
+        have_ab = all(getattr(traj, k, None) is not None for k in ("Ad", "Bd", "gd"))
+        have_raw = getattr(traj, "m", None) is not None and getattr(traj, "I_com_world", None) is not None
+        use_ab = have_ab if self.dynamics == "auto" else (self.dynamics == "traj")
+        if use_ab:
+            if not have_ab:
+                raise _lib.CmpcError("dynamics='traj' needs traj.Ad, traj.Bd and traj.gd")
+            t["Ad"] = self._dev(traj.Ad, (B, 12, 12))
+            t["Bd"] = self._dev(traj.Bd, (B, N, 12, 12))
+            t["gd"] = self._dev(traj.gd, (B, 12))
+        else:
+            if not have_raw:
+                raise _lib.CmpcError("dynamics='device' needs traj.m, traj.I_com_world and the foot lever arms")
+            m = traj.m
+            if not isinstance(m, torch.Tensor) and np.ndim(m) == 0:
+                m = np.full(B, float(m))
+            t["mass"] = self._dev(m, (B,))
+            t["I_world"] = self._dev(traj.I_com_world, (B, 3, 3))
+            rf = getattr(traj, "r_foot", None)
+            if rf is None:
+                legs = [getattr(traj, name) for name in _LEG_FIELDS]
+                if isinstance(legs[0], torch.Tensor):
+                    rf = torch.stack([l.reshape(B, 3, N) for l in legs], dim=1)
+                else:
+                    rf = np.stack([np.asarray(l, dtype=np.float64).reshape(B, 3, N) for l in legs], axis=1)
+            t["r_foot"] = self._dev(rf, (B, 4, 3, N))
+            t["dt"] = float(getattr(traj, "dt", None) or (1.0 / getattr(traj, "gait_hz", 3.0)) / N)
+        # contact mask: the table the reference carries (com_trajectory.py:106), else computed here
+        ct = getattr(traj, "contact_table", None)
+        if ct is not None:
+            if isinstance(ct, torch.Tensor):
+                c = ct.to(device=self.device, dtype=torch.int32).reshape(B, 4, N).contiguous()
+            else:
+                c = torch.from_numpy(np.ascontiguousarray(np.asarray(ct).astype(np.int32))).to(self.device)
+                c = c.reshape(B, 4, N).contiguous()
+            t["ct"] = c
+            check(self._lib.cmpc_pack_contact(self._h, B, c.data_ptr(), self._mask.data_ptr(), stream))
+        else:
+            tn = getattr(traj, "time_now", None)
+            if tn is None:
+                raise _lib.CmpcError("traj needs contact_table or time_now (+ gait_hz, gait_duty)")
+            if not isinstance(tn, torch.Tensor) and np.ndim(tn) == 0:
+                tn = np.full(B, float(tn))
+            t["t0"] = self._dev(tn, (B,))
+            dt = float(getattr(traj, "dt", None) or (1.0 / traj.gait_hz) / N)
+            off = _lib.darr(getattr(traj, "phase_offset", PHASE_OFFSET))
+            check(self._lib.cmpc_contact_table(self._h, B, t["t0"].data_ptr(), dt, float(traj.gait_hz),
+                                               float(traj.gait_duty), off, self._mask.data_ptr(), stream))
+        return t, use_ab
+
+    # ------------------------------------------------------------------------------------------
+    def solve_QP(self, go2, traj, verbose: bool = False):
+        """One MPC cycle for every robot in ``traj`` (centroidal_mpc.py:69-120)."""
+        t0 = time.perf_counter()
+        B0 = self._batch_of(traj)
+        B = max(B0, 1)
+        N = self.N
+        if int(traj.N) != N:
+            raise _lib.CmpcError(f"traj.N = {traj.N} but the solver was built for N = {N}")
+        self._alloc_state(B)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            t, use_ab = self._gather(traj, B, stream)
+            torch.cuda.current_stream().synchronize()
+            t1 = time.perf_counter()
+            p = lambda k: t[k].data_ptr() if k in t else None
+            check(self._lib.cmpc_solve(
+                self._h, B, p("Ad"), p("Bd"), p("gd"), p("x0"), p("x_ref"), p("r_foot"), p("I_world"), p("mass"),
+                float(t.get("dt", 0.0)), self._mask.data_ptr(), int(self._warm),
+                self._u.data_ptr(), self._y.data_ptr(), self._rho.data_ptr(), self._X.data_ptr(),
+                self._nu.data_ptr(), self._status.data_ptr(), self._iters.data_ptr(), self._stats.data_ptr(),
+                stream))
+            torch.cuda.current_stream().synchronize()   # the reference call is blocking (centroidal_mpc.py:98)
+        t2 = time.perf_counter()
+        self.update_time = (t1 - t0) * 1e3      # ms, as centroidal_mpc.py:102-105
+        self.solve_time = (t2 - t1) * 1e3
+        if OPTS.get("warm_start_primal", True):
+            self._warm = True
+
+        batched = B0 > 0
+        sq = (lambda a: a) if batched else (lambda a: a[0])
+        zeros = torch.zeros(B, 12 * N, dtype=torch.float64, device=self.device)
+        sol = MPCSolution()
+        sol["x"] = _DM(sq(torch.cat([self._X, self._u], dim=1)), batched)
+        sol["lam_x"] = _DM(sq(torch.cat([zeros, self._y[:, :12 * N]], dim=1)), batched)
+        sol["lam_a"] = _DM(sq(torch.cat([self._nu, self._y[:, 12 * N:]], dim=1)), batched)
+        sol["cost"] = _DM(sq(self._stats[:, 2:3].clone()), batched)
+        sol["u"] = sq(self._u.view(B, N, 12).transpose(1, 2))       # (B,12,N): U_opt of test_MPC.py:192
+        sol["X"] = sq(self._X.view(B, N, 12).transpose(1, 2))
+        sol["status"] = sq(self._status)
+        sol["iters"] = sq(self._iters)
+        sol["stats"] = sq(self._stats)
+        sol["r_prim"] = sq(self._stats[:, 0])
+        sol["r_dual"] = sq(self._stats[:, 1])
+        self.x_prev, self.lam_x_prev, self.lam_a_prev = sol["x"], sol["lam_x"], sol["lam_a"]
+        self.last_stats = self._stats
+        if verbose:
+            st = self._status.cpu().numpy()
+            print(f"[QP SOLVER] update (gather + contact mask) takes {self.update_time:.3f} ms")
+            print(f"[QP SOLVER] solver takes {self.solve_time:.3f} ms for {B} robot(s)")
+            tot = (t2 - t0)
+            print(f"[QP SOLVER] total time = {tot * 1e3:.3f} ms  ({B / tot:.1f} QPs/s)")
+            print(f"[QP SOLVER] status: solved {int((st == 1).sum())}/{B}, "
+                  f"max iters {int(self._iters.max())}")
+        return sol
+
+    # ------------------------------------------------------------------------------------------
+    def solve_host(self, x0, x_ref, r_foot, I_world, mass, t0, dt, gait_hz=3.0, duty=0.6,
+                   phase_offset=PHASE_OFFSET, out=None):
+        """Whole cycle on HOST buffers through ``cmpc_solve_host`` (chunked, copy/compute overlapped).
+
+        Inputs: C-contiguous float64 numpy arrays or CPU torch tensors (pinned memory gives true
+        overlap).  Returns ``(u (B,12N), status (B), iters (B))`` as numpy views of ``out`` buffers.
+        """
+        def host_ptr(a, n):
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == n
+                return a.data_ptr()
+            a = np.asarray(a)
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == n
+            return a.ctypes.data
+        N = self.N
+        B = int(np.prod(tuple(mass.shape)))
+        if out is None:
+            out = (torch.empty(B, 12 * N, dtype=torch.float64).pin_memory(),
+                   torch.empty(B, dtype=torch.int32).pin_memory(),
+                   torch.empty(B, dtype=torch.int32).pin_memory())
+        u, st, it = out
+        check(self._lib.cmpc_solve_host(
+            self._h, B, host_ptr(x0, B * 12), host_ptr(x_ref, B * 12 * N), host_ptr(r_foot, B * 12 * N),
+            host_ptr(I_world, B * 9), host_ptr(mass, B), host_ptr(t0, B), float(dt), float(gait_hz), float(duty),
+            _lib.darr(phase_offset), int(self._warm_host if hasattr(self, "_warm_host") else 0),
+            u.data_ptr(), st.data_ptr(), it.data_ptr()))
+        self._warm_host = 1 if OPTS.get("warm_start_primal", True) else 0
+        return u, st, it
+
+    def host_stats(self, B):
+        s = np.empty((B, _lib.NSTAT))
+        check(self._lib.cmpc_host_stats(self._h, B, s.ctypes.data))
+        return s

@@ -1,0 +1,528 @@
+// cmpc.cu -- CUDA kernels (sm_100a) and the C-ABI of include/cmpc.h.
+//
+// Kernels:
+//   contact_table_kernel   gait.py:26-37                      one thread per robot
+//   dynamics_kernel        com_trajectory.py:221-286          one thread per (robot, step)
+//   build_kernel           centroidal_mpc.py:235-303 (condensed)   one CTA per robot (diagnostic)
+//   solve_kernel           centroidal_mpc.py:69-120           one CTA per robot, everything in smem
+//   fp64_peak_kernel / smem_peak_kernel    roofline denominators measured on the box
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cmpc.h"
+#include "cmpc_core.cuh"
+
+using namespace cmpc;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const std::string& m) { g_err = m; return -1; }
+
+#define CU_TRY(x)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (x);                                                             \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(std::string(#x) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+constexpr int kThreads = 256;
+
+struct BatchIn {
+    const double* Ad; const double* Bd; const double* gd;
+    const double* x0; const double* x_ref; const double* r_foot; const double* I_world; const double* mass;
+    double dt;
+    const uint64_t* mask;
+    int N, W;
+};
+
+struct BatchOut {
+    double* u; double* y; double* rho; double* X; double* nu;
+    int32_t* status; int32_t* iters; double* stats;
+};
+
+__device__ __forceinline__ QpIn qp_in(const BatchIn& bi, int b) {
+    QpIn in;
+    const int N = bi.N;
+    in.Ad = bi.Ad ? bi.Ad + (size_t)b * 144 : nullptr;
+    in.Bd = bi.Bd ? bi.Bd + (size_t)b * N * 144 : nullptr;
+    in.gd = bi.gd ? bi.gd + (size_t)b * 12 : nullptr;
+    in.x0 = bi.x0 + (size_t)b * 12;
+    in.x_ref = bi.x_ref + (size_t)b * 12 * N;
+    in.r_foot = bi.r_foot ? bi.r_foot + (size_t)b * 12 * N : nullptr;
+    in.I_world = bi.I_world ? bi.I_world + (size_t)b * 9 : nullptr;
+    in.mass = bi.mass ? bi.mass[b] : 1.0;
+    in.dt = bi.dt;
+    in.mask = bi.mask ? bi.mask + (size_t)b * bi.W : nullptr;
+    in.N = N;
+    return in;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void contact_table_kernel(int B, int N, int W, const double* __restrict__ t0, double dt, double period,
+                                     double duty, double o0, double o1, double o2, double o3,
+                                     uint64_t* __restrict__ mask) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double off[4] = {o0, o1, o2, o3};
+    const double t = t0[b];
+    uint64_t words[3] = {0, 0, 0};
+    for (int leg = 0; leg < 4; ++leg)
+        for (int k = 0; k < N; ++k) {
+            const int bit = leg * N + k;
+            if (stance_bit(t, dt, k, period, off[leg], duty)) words[bit >> 6] |= (1ull << (bit & 63));
+        }
+    for (int wv = 0; wv < W; ++wv) mask[(size_t)b * W + wv] = words[wv];
+}
+
+__global__ void pack_contact_kernel(int B, int N, int W, const int32_t* __restrict__ table, uint64_t* __restrict__ mask) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    uint64_t words[3] = {0, 0, 0};
+    for (int bit = 0; bit < 4 * N; ++bit)
+        if (table[(size_t)b * 4 * N + bit] != 0) words[bit >> 6] |= (1ull << (bit & 63));
+    for (int wv = 0; wv < W; ++wv) mask[(size_t)b * W + wv] = words[wv];
+}
+
+__global__ void dynamics_kernel(int B, int N, const double* __restrict__ x_ref, const double* __restrict__ r_foot,
+                                const double* __restrict__ I_world, const double* __restrict__ mass, double dt,
+                                double* __restrict__ Ad, double* __restrict__ Bd, double* __restrict__ gd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * N) return;
+    const int b = idx / N, k = idx - b * N;
+    DynCommon d;
+    dyn_common(d, x_ref + (size_t)b * 12 * N, N, I_world + (size_t)b * 9, mass[b], dt);
+    if (k == 0) {
+        for (int i = 0; i < 144; ++i) Ad[(size_t)b * 144 + i] = dyn_Ad(d, i / 12, i % 12);
+        double g[12];
+        dyn_gd(d, g);
+        for (int i = 0; i < 12; ++i) gd[(size_t)b * 12 + i] = g[i];
+    }
+    double* out = Bd + ((size_t)b * N + k) * 144;
+    for (int leg = 0; leg < 4; ++leg) {
+        double r[3];
+        for (int a = 0; a < 3; ++a) r[a] = r_foot[(size_t)b * 12 * N + (size_t)(leg * 3 + a) * N + k];
+        for (int comp = 0; comp < 3; ++comp) {
+            double col[12];
+            dyn_Bd_col(d, r, comp, col);
+            for (int a = 0; a < 12; ++a) out[a * 12 + 3 * leg + comp] = col[a];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+build_kernel(Params p, BatchIn bi, int B, int nfmax, double* __restrict__ H, double* __restrict__ g,
+             double* hp_scratch, size_t hp_stride) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Ws w;
+    ws_carve(w, smem, bi.N, nfmax, hp_scratch ? hp_scratch + (size_t)blockIdx.x * hp_stride : nullptr);
+    Cta c;
+    c.tid = threadIdx.x; c.nt = blockDim.x; c.warp = 0;
+    const int n = 12 * bi.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        QpIn in = qp_in(bi, b);
+        build_dense_one(c, p, in, w, nfmax, H + (size_t)b * n * n, g + (size_t)b * n);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+solve_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hp_scratch, size_t hp_stride) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Ws w;
+    ws_carve(w, smem, bi.N, nfmax, hp_scratch ? hp_scratch + (size_t)blockIdx.x * hp_stride : nullptr);
+    Cta c;
+    c.tid = threadIdx.x; c.nt = blockDim.x; c.warp = 0;
+    const int N = bi.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        QpIn in = qp_in(bi, b);
+        QpOut o;
+        o.u = bo.u + (size_t)b * 12 * N;
+        o.y = bo.y + (size_t)b * 28 * N;
+        o.rho = bo.rho ? bo.rho + b : nullptr;
+        o.X = bo.X ? bo.X + (size_t)b * 12 * N : nullptr;
+        o.nu = bo.nu ? bo.nu + (size_t)b * 12 * N : nullptr;
+        o.status = bo.status + b;
+        o.iters = bo.iters + b;
+        o.stats = bo.stats + (size_t)b * NSTAT;
+        solve_one(c, p, in, o, w, nfmax, warm);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roofline denominators: dependent-free DFMA streams and shared-memory 8-byte reads.
+// ---------------------------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, s = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, s); a1 = fma(a1, m, s); a2 = fma(a2, m, s); a3 = fma(a3, m, s);
+        a4 = fma(a4, m, s); a5 = fma(a5, m, s); a6 = fma(a6, m, s); a7 = fma(a7, m, s);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void smem_peak_kernel(double* out, int iters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2* s = reinterpret_cast<double2*>(smem);
+    const int nvec = 4096;   // 64 KB
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) s[i] = make_double2(i, 1.0);
+    __syncthreads();
+    double acc = 0.0;
+    int idx = threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double2 v = s[(idx + u * blockDim.x) & (nvec - 1)];
+            acc += v.x + v.y;
+        }
+        idx = (idx + 8 * blockDim.x) & (nvec - 1);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Handle
+// ---------------------------------------------------------------------------------------------
+struct cmpc_handle {
+    int N = 16, W = 1, max_batch = 0, device = 0;
+    int nfmax = 64;        // largest number of stance foot-steps any robot may have
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    Params p;
+    double* hp_scratch = nullptr;   // packed-matrix scratch when it does not fit shared memory
+    size_t hp_stride = 0;
+    int hp_ctas = 0;
+    // device-resident state for the *_host entry
+    struct HostPath {
+        bool ready = false;
+        double *x0 = nullptr, *x_ref = nullptr, *r_foot = nullptr, *I_world = nullptr, *mass = nullptr, *t0 = nullptr;
+        uint64_t* mask = nullptr;
+        double *u = nullptr, *y = nullptr, *rho = nullptr, *stats = nullptr;
+        int32_t *status = nullptr, *iters = nullptr;
+        cudaStream_t s[2] = {nullptr, nullptr};
+    } hp;
+};
+
+namespace {
+
+void default_params(Params& p) {
+    const double Q[12] = {1, 1, 50, 10, 20, 1, 2, 2, 1, 1, 1, 1};   // centroidal_mpc.py:12
+    for (int i = 0; i < 12; ++i) { p.Q[i] = Q[i]; p.R[i] = 1e-5; }  // centroidal_mpc.py:13
+    p.mu = 0.8;            // centroidal_mpc.py:15
+    p.fz_min = 10.0;       // centroidal_mpc.py:127
+    p.eps_abs = 1e-4;      // centroidal_mpc.py:25-26 (OPTS)
+    p.eps_rel = 1e-4;
+    p.max_iter = 1000;     // :27
+    p.rho0 = 1e-4;         // OSQP's 0.1 is 3 orders off for this problem
+    p.sigma = 1e-6;
+    p.alpha = 1.6;
+    p.mode = CMPC_MODE_ACTIVE_SET;
+    p.polish = 0;
+    p.check_termination = 10;       // :31
+    p.adaptive_rho_interval = 25;   // :32
+    p.pdas_max_iter = 16;
+}
+
+size_t smem_needed(int N, int nfmax, bool hp_external) {
+    Ws w;
+    unsigned char* base = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20));
+    static double dummy;
+    return ws_carve(w, base, N, nfmax, hp_external ? &dummy : nullptr);
+}
+
+// Decide where the packed matrix lives and make sure scratch exists.  Returns smem bytes.
+int plan_launch(cmpc_handle* h, int nfmax, const void* kernel, size_t* smem_out, double** hp, size_t* stride, int* grid_cap) {
+    size_t need = smem_needed(h->N, nfmax, false);
+    *hp = nullptr; *stride = 0; *grid_cap = 0;
+    if (need > h->smem_optin) {
+        need = smem_needed(h->N, nfmax, true);
+        if (need > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
+        const size_t nmax = 3 * (size_t)nfmax;
+        const size_t st = ((nmax + 1) * (nmax + 2) / 2 + 1) & ~(size_t)1;
+        const int ctas = h->sm_count * 2;
+        if (h->hp_stride < st || h->hp_ctas < ctas) {
+            if (h->hp_scratch) cudaFree(h->hp_scratch);
+            h->hp_scratch = nullptr;
+            CU_TRY(cudaMalloc(&h->hp_scratch, st * ctas * sizeof(double)));
+            h->hp_stride = st; h->hp_ctas = ctas;
+        }
+        *hp = h->hp_scratch; *stride = h->hp_stride; *grid_cap = h->hp_ctas;
+    }
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    *smem_out = need;
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* cmpc_last_error(void) { return g_err.c_str(); }
+const char* cmpc_version(void) { return "cmpc-b200 0.1.0 (sm_100a)"; }
+long long cmpc_launch_count(void) { return g_launches.load(); }
+
+int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
+    if (!out) return fail("out is null");
+    if (N < 1 || N > 48) return fail("horizon N must be in [1, 48]");
+    if (max_batch < 1) return fail("max_batch must be >= 1");
+    CU_TRY(cudaSetDevice(device));
+    cmpc_handle* h = new cmpc_handle();
+    h->N = N; h->W = (4 * N + 63) / 64; h->max_batch = max_batch; h->device = device;
+    h->nfmax = 4 * N;
+    default_params(h->p);
+    int v = 0;
+    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    h->sm_count = v;
+    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    h->smem_optin = (size_t)v;
+    *out = h;
+    return 0;
+}
+
+int cmpc_destroy(cmpc_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->hp_scratch) cudaFree(h->hp_scratch);
+    auto& q = h->hp;
+    void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto s : q.s) if (s) cudaStreamDestroy(s);
+    delete h;
+    return 0;
+}
+
+int cmpc_set_params(cmpc_handle* h, const double Q[12], const double R[12], double mu, double fz_min,
+                    double eps_abs, double eps_rel, int max_iter, double rho0, double sigma, double alpha,
+                    int mode, int polish, int check_termination, int adaptive_rho_interval) {
+    if (!h) return fail("null handle");
+    if (Q) for (int i = 0; i < 12; ++i) h->p.Q[i] = Q[i];
+    if (R) for (int i = 0; i < 12; ++i) h->p.R[i] = R[i];
+    for (int i = 0; i < 12; ++i) if (!(h->p.R[i] > 0.0) || !(h->p.Q[i] >= 0.0)) return fail("need Q >= 0 and R > 0");
+    if (!(mu > 0.0) || !(eps_abs > 0.0) || !(eps_rel >= 0.0) || max_iter < 1 || !(rho0 > 0.0) || !(sigma > 0.0) ||
+        !(alpha > 0.0 && alpha < 2.0) || check_termination < 1)
+        return fail("invalid solver parameter");
+    if (mode != CMPC_MODE_ADMM && mode != CMPC_MODE_ACTIVE_SET) return fail("unknown mode");
+    h->p.mu = mu; h->p.fz_min = fz_min; h->p.eps_abs = eps_abs; h->p.eps_rel = eps_rel; h->p.max_iter = max_iter;
+    h->p.rho0 = rho0; h->p.sigma = sigma; h->p.alpha = alpha; h->p.mode = mode; h->p.polish = polish;
+    h->p.check_termination = check_termination; h->p.adaptive_rho_interval = adaptive_rho_interval;
+    return 0;
+}
+
+int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
+    if (!h) return fail("null handle");
+    if (nfmax < 4) nfmax = 4;
+    if (nfmax > 4 * h->N) nfmax = 4 * h->N;
+    h->nfmax = nfmax;
+    return 0;
+}
+
+int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz, double duty,
+                       const double phase_offset[4], uint64_t* mask_out, void* stream) {
+    if (!h || !t0 || !mask_out || !phase_offset) return fail("null argument");
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    const double period = 1 / gait_hz;   // gait.py:17
+    const int tpb = 128;
+    contact_table_kernel<<<(B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
+        B, h->N, h->W, t0, dt, period, duty, phase_offset[0], phase_offset[1], phase_offset[2], phase_offset[3], mask_out);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_pack_contact(cmpc_handle* h, int B, const int32_t* table, uint64_t* mask_out, void* stream) {
+    if (!h || !table || !mask_out) return fail("null argument");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    const int tpb = 128;
+    pack_contact_kernel<<<(B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(B, h->N, h->W, table, mask_out);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_dynamics(cmpc_handle* h, int B, const double* x_ref, const double* r_foot, const double* I_world,
+                  const double* mass, double dt, double* Ad, double* Bd, double* gd, void* stream) {
+    if (!h || !x_ref || !r_foot || !I_world || !mass || !Ad || !Bd || !gd) return fail("null argument");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    const int tpb = 128, total = B * h->N;
+    dynamics_kernel<<<(total + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(B, h->N, x_ref, r_foot, I_world, mass, dt, Ad, Bd, gd);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int check_inputs(const double* Ad, const double* Bd, const double* gd, const double* x0, const double* x_ref,
+                        const double* r_foot, const double* I_world, const double* mass) {
+    if (!x0 || !x_ref) return fail("x0 and x_ref are required");
+    const bool have_ab = Ad && Bd && gd;
+    const bool have_raw = r_foot && I_world && mass;
+    if (!have_ab && !have_raw) return fail("need either (Ad,Bd,gd) or (r_foot,I_world,mass)");
+    if ((Ad || Bd || gd) && !have_ab) return fail("Ad, Bd and gd must be given together");
+    return 0;
+}
+
+int cmpc_build(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd, const double* x0,
+               const double* x_ref, const double* r_foot, const double* I_world, const double* mass, double dt,
+               double* H, double* g, void* stream) {
+    if (!h || !H || !g) return fail("null argument");
+    if (check_inputs(Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass)) return -1;
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    BatchIn bi{Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, nullptr, h->N, h->W};
+    size_t smem; double* hp; size_t stride; int cap;
+    if (plan_launch(h, 4 * h->N, (const void*)build_kernel, &smem, &hp, &stride, &cap)) return -1;
+    const int grid = cap ? (B < cap ? B : cap) : B;
+    build_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, B, 4 * h->N, H, g, hp, stride);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd, const double* x0,
+               const double* x_ref, const double* r_foot, const double* I_world, const double* mass, double dt,
+               const uint64_t* mask, int warm, double* u, double* y, double* rho, double* X, double* nu,
+               int32_t* status, int32_t* iters, double* stats, void* stream) {
+    if (!h || !u || !y || !status || !iters || !stats) return fail("null argument");
+    if (check_inputs(Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass)) return -1;
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    BatchIn bi{Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, mask, h->N, h->W};
+    BatchOut bo{u, y, rho, X, nu, status, iters, stats};
+    size_t smem; double* hp; size_t stride; int cap;
+    if (plan_launch(h, h->nfmax, (const void*)solve_kernel, &smem, &hp, &stride, &cap)) return -1;
+    const int grid = cap ? (B < cap ? B : cap) : B;
+    solve_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref, const double* r_foot,
+                    const double* I_world, const double* mass, const double* t0, double dt, double gait_hz,
+                    double duty, const double phase_offset[4], int warm, double* u, int32_t* status, int32_t* iters) {
+    if (!h || !x0 || !x_ref || !r_foot || !I_world || !mass || !t0 || !phase_offset || !u || !status || !iters)
+        return fail("null argument");
+    if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    const int N = h->N;
+    auto& q = h->hp;
+    if (!q.ready) {
+        const size_t mb = (size_t)h->max_batch;
+        CU_TRY(cudaMalloc(&q.x0, mb * 12 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.x_ref, mb * 12 * N * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.r_foot, mb * 12 * N * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.I_world, mb * 9 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.mass, mb * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.t0, mb * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.mask, mb * h->W * sizeof(uint64_t)));
+        CU_TRY(cudaMalloc(&q.u, mb * 12 * N * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.y, mb * 28 * N * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.rho, mb * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.stats, mb * CMPC_NSTAT * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.status, mb * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&q.iters, mb * sizeof(int32_t)));
+        CU_TRY(cudaMemset(q.rho, 0, mb * sizeof(double)));
+        CU_TRY(cudaMemset(q.u, 0, mb * 12 * N * sizeof(double)));
+        CU_TRY(cudaMemset(q.y, 0, mb * 28 * N * sizeof(double)));
+        for (auto& s : q.s) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        q.ready = true;
+    }
+    // chunks sized so that copies of one chunk hide behind the solve of the other
+    const int chunk = B <= 4096 ? B : 8192;
+    int ci = 0;
+    for (int lo = 0; lo < B; lo += chunk, ++ci) {
+        const int nb = (B - lo) < chunk ? (B - lo) : chunk;
+        cudaStream_t s = q.s[ci & 1];
+        const size_t o = (size_t)lo;
+        CU_TRY(cudaMemcpyAsync(q.x0 + o * 12, x0 + o * 12, (size_t)nb * 12 * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(q.x_ref + o * 12 * N, x_ref + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(q.r_foot + o * 12 * N, r_foot + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(q.I_world + o * 9, I_world + o * 9, (size_t)nb * 9 * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(q.mass + o, mass + o, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(q.t0 + o, t0 + o, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (cmpc_contact_table(h, nb, q.t0 + o, dt, gait_hz, duty, phase_offset, q.mask + o * h->W, s)) return -1;
+        if (cmpc_solve(h, nb, nullptr, nullptr, nullptr, q.x0 + o * 12, q.x_ref + o * 12 * N, q.r_foot + o * 12 * N,
+                       q.I_world + o * 9, q.mass + o, dt, q.mask + o * h->W, warm, q.u + o * 12 * N, q.y + o * 28 * N,
+                       q.rho + o, nullptr, nullptr, q.status + o, q.iters + o, q.stats + o * CMPC_NSTAT, s))
+            return -1;
+        CU_TRY(cudaMemcpyAsync(u + o * 12 * N, q.u + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(status + o, q.status + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpyAsync(iters + o, q.iters + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(q.s[0]));
+    CU_TRY(cudaStreamSynchronize(q.s[1]));
+    return 0;
+}
+
+/* stats of the last cmpc_solve_host call stay on the device; copy them out on request */
+int cmpc_host_stats(cmpc_handle* h, int B, double* stats_host) {
+    if (!h || !stats_host || !h->hp.ready) return fail("no host-path state");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaMemcpy(stats_host, h->hp.stats, (size_t)B * CMPC_NSTAT * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs) {
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* out = nullptr;
+    const int tpb = 256, blocks = sms * 8;
+    CU_TRY(cudaMalloc(&out, (size_t)tpb * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    if (fp64_tflops) {
+        const int iters = 1 << 14;
+        fp64_peak_kernel<<<blocks, tpb>>>(out, 64);
+        CU_TRY(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, tpb>>>(out, iters);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        g_launches += 2;
+        *fp64_tflops = 2.0 * 8.0 * iters * (double)tpb * blocks / (ms * 1e-3) / 1e12;
+    }
+    if (smem_gbs) {
+        const int iters = 1 << 12;
+        const size_t smem = 64 * 1024;
+        CU_TRY(cudaFuncSetAttribute((const void*)smem_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int b2 = sms * 3;
+        smem_peak_kernel<<<b2, tpb, smem>>>(out, 8);
+        CU_TRY(cudaEventRecord(e0));
+        smem_peak_kernel<<<b2, tpb, smem>>>(out, iters);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        g_launches += 2;
+        *smem_gbs = 16.0 * 8.0 * iters * (double)tpb * b2 / (ms * 1e-3) / 1e9;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

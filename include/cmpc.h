@@ -1,0 +1,134 @@
+/* cmpc.h -- C-ABI of the B200-native batched Go2 convex-MPC hot path.
+ *
+ * The reference (ltinphan/convex-mpc-unitree-go2 v0.3.0) has no FFI of its own: its boundary is
+ * the Python class `CentroidalMPC` (convex_mpc/centroidal_mpc.py:40-120) which calls CasADi->OSQP
+ * in-process.  These entry points are what a ctypes binding for that class binds;
+ * each one cites the reference code it replaces.  All array arguments are raw pointers,
+ * row-major, leading batch dimension B, FP64 unless stated.  `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream).  Every function returns 0 on success, <0 on error
+ * (cmpc_last_error() gives the message).  Functions whose name ends in `_host` take HOST pointers
+ * and do their own H2D/D2H; all others take DEVICE pointers and only enqueue work on `stream`.
+ *
+ * Variable / row orderings (identical to the reference):
+ *   u     (B, 12N)   force vector in the order of w[12N:] (test_MPC.py:189-192):
+ *                    index 12k + 3 leg + c, legs FL FR RL RR, c = x,y,z, world frame.
+ *   X     (B, 12N)   predicted states x_1..x_N in the order of w[:12N], index 12k + i.
+ *   y     (B, 28N)   duals of the condensed QP rows: [0,12N) box rows on u (== lam_x[12N:]),
+ *                    [12N,28N) friction rows 16k + 4 leg + face, faces +fx,-fx,+fy,-fy
+ *                    (== lam_a[12N:], centroidal_mpc.py:324-359).  Sign: y>0 at upper bounds.
+ *   nu    (B, 12N)   co-states == lam_a[:12N] (dynamics equality rows, centroidal_mpc.py:287-303).
+ *   mask  (B, W)     uint64 words, W = ceil(4N/64), bit leg*N + k = 1 for stance (gait.py:26-37).
+ */
+#ifndef CMPC_H
+#define CMPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmpc_handle cmpc_handle;
+
+/* solver status per QP (values follow OSQP's constants) */
+#define CMPC_SOLVED               1
+#define CMPC_SOLVED_INACCURATE    2
+#define CMPC_MAX_ITER_REACHED    -2
+#define CMPC_NON_CVX             -7
+#define CMPC_TOO_MANY_FEET       -20
+
+/* solver modes */
+#define CMPC_MODE_ADMM            0   /* OSQP-equivalent ADMM only (reference OPTS: polish off)      */
+#define CMPC_MODE_ACTIVE_SET      1   /* exact active-set (polish-first) with ADMM fallback (default) */
+
+/* per-QP statistics record, (B, CMPC_NSTAT) doubles */
+#define CMPC_NSTAT 8
+#define CMPC_STAT_RPRIM   0   /* max constraint violation (N)                 */
+#define CMPC_STAT_RDUAL   1   /* |H u + g + A'y|_inf                          */
+#define CMPC_STAT_OBJ     2   /* 1/2 w'Hw + g'w of the reference QP ("cost")    */
+#define CMPC_STAT_NFREE   3   /* number of stance (free) force variables      */
+#define CMPC_STAT_NACT    4   /* active inequality rows at the solution       */
+#define CMPC_STAT_RHO     5   /* final ADMM rho                               */
+#define CMPC_STAT_ASITERS 6   /* active-set iterations                        */
+#define CMPC_STAT_PATH    7   /* 0 unconstrained, 1 active-set, 2 ADMM, 3 ADMM+polish */
+
+/* Replaces CentroidalMPC.__init__ (centroidal_mpc.py:41-67): allocates nothing on the device but
+ * fixes the horizon N (16, 32 or 48 ...; <= 48) and the largest batch the handle will see.     */
+int cmpc_create(int N, int max_batch, int device, cmpc_handle** out);
+int cmpc_destroy(cmpc_handle* h);
+
+/* Module constants of centroidal_mpc.py:12-38 (COST_MATRIX_Q/R diagonals, MU, fz_min :127, OPTS). */
+int cmpc_set_params(cmpc_handle* h, const double Q[12], const double R[12], double mu, double fz_min,
+                    double eps_abs, double eps_rel, int max_iter, double rho0, double sigma,
+                    double alpha, int mode, int polish, int check_termination,
+                    int adaptive_rho_interval);
+
+/* Upper bound on stance foot-steps per robot (<= 4N, default 4N).  The reference's QP always has
+ * 12N force variables with swing forces pinned to zero by lbx = ubx = 0 (centroidal_mpc.py:150-161);
+ * the fused solver eliminates them, and a tighter bound (e.g. 4*(floor(duty*N)+1) for a periodic
+ * gait) lets two CTAs share one SM.  Robots exceeding it get status CMPC_TOO_MANY_FEET.          */
+int cmpc_set_max_stance(cmpc_handle* h, int nfmax);
+
+/* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
+int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
+                       double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);
+
+/* traj.contact_table as the reference stores it, (B,4,N) int32 with 1 = stance
+ * (com_trajectory.py:106), packed into the mask words the solver reads.                          */
+int cmpc_pack_contact(cmpc_handle* h, int B, const int32_t* table, uint64_t* mask_out, void* stream);
+
+/* ComTraj._continuousDynamics + _discreteDynamics (com_trajectory.py:221-286), closed form.
+ * x_ref (B,12,N), r_foot (B,4,3,N), I_world (B,3,3), mass (B)  ->  Ad (B,12,12), Bd (B,N,12,12),
+ * gd (B,12).                                                                                     */
+int cmpc_dynamics(cmpc_handle* h, int B, const double* x_ref, const double* r_foot,
+                  const double* I_world, const double* mass, double dt,
+                  double* Ad, double* Bd, double* gd, void* stream);
+
+/* Condensed QP data of centroidal_mpc.py:235-303 after eliminating the dynamics rows:
+ * H = 2(Bqp' L Bqp + K) (B,12N,12N) dense symmetric, g (B,12N), for the full variable set.
+ * Either (Ad,Bd,gd) are given (drop-in path: traj carries them) or they are NULL and the raw
+ * inputs (r_foot, I_world, mass, dt) are used.  Diagnostic / parity entry: the fused solver never
+ * writes H to HBM.                                                                              */
+int cmpc_build(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd,
+               const double* x0, const double* x_ref, const double* r_foot, const double* I_world,
+               const double* mass, double dt, double* H, double* g, void* stream);
+
+/* CentroidalMPC.solve_QP (centroidal_mpc.py:69-120): build + solve, fused, one CTA per robot.
+ * Inputs as in cmpc_build plus mask (B,W).  In/out warm-start state: u (B,12N), y (B,28N), rho (B)
+ * (warm != 0 -> use them as the initial guess, as centroidal_mpc.py:92-95 does).
+ * Optional outputs (may be NULL): X (B,12N), nu (B,12N).  status (B) int32, iters (B) int32,
+ * stats (B, CMPC_NSTAT).                                                                         */
+int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd,
+               const double* x0, const double* x_ref, const double* r_foot, const double* I_world,
+               const double* mass, double dt, const uint64_t* mask, int warm,
+               double* u, double* y, double* rho, double* X, double* nu,
+               int32_t* status, int32_t* iters, double* stats, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): chunked H2D -> contact table -> solve -> D2H,
+ * copies overlapped with compute on two streams.  Raw-input path only (Ad/Bd computed on device).
+ * t0 (B) host.  Outputs u (B,12N), status (B), iters (B) on the host; warm-start state stays
+ * resident on the device inside the handle between calls (warm != 0 reuses it).                 */
+int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref,
+                    const double* r_foot, const double* I_world, const double* mass,
+                    const double* t0, double dt, double gait_hz, double duty,
+                    const double phase_offset[4], int warm,
+                    double* u, int32_t* status, int32_t* iters);
+
+/* Per-QP statistics (B, CMPC_NSTAT) of the last cmpc_solve_host call, copied to the host. */
+int cmpc_host_stats(cmpc_handle* h, int B, double* stats_host);
+
+/* Number of kernels launched by this library since process start (bench.py "gpu_launches"). */
+long long cmpc_launch_count(void);
+
+/* Micro-benchmarks used for the roofline denominators that MEASURED_PEAKS.json lacks
+ * (SURVEY.md section 8d): FP64 FMA throughput (TFLOP/s) and shared-memory read bandwidth (GB/s). */
+int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs);
+
+const char* cmpc_last_error(void);
+const char* cmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMPC_H */

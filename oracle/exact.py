@@ -81,6 +81,12 @@ def solve_exact(H, g, A, l, u, max_refine=60, tol=1e-9):
     n = H.shape[0]
     free, fixed, xf, rows, Hr, gr, Ar, lr, ur = _reduce(H, g, A, l, u)
     m = Ar.shape[0]
+    if Hr.shape[0] == 0:
+        # every variable is fixed (all legs in swing): nothing to optimise
+        U = xf.copy()
+        yfull = np.zeros(A.shape[0])
+        yfull[:n] = -(H @ U + g)
+        return dict(U=U, y=yfull, iters=0, refine=0, ok=True)
     x, y, z, it = admm_dense(Hr, gr, Ar, lr, ur, rho=1e-4, iters=3000, eps=1e-8)
     Ax = Ar @ x
     scale = 1.0 + np.abs(Ax)

@@ -1,0 +1,106 @@
+// cmpc_emul.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel source (csrc/cmpc_core.cuh) for the host with a ONE-THREAD CTA, so that the
+// CPU test-suite can check the *kernel logic* (indexing, recursions, active-set / ADMM control
+// flow) against the oracle without a GPU.  It is not linked into libcmpc.so, it is not importable
+// from the package, and nothing in the product path can reach it.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_core.cuh"
+
+using namespace cmpc;
+
+extern "C" {
+
+void emul_default_params(Params* p) {
+    const double Q[12] = {1, 1, 50, 10, 20, 1, 2, 2, 1, 1, 1, 1};
+    for (int i = 0; i < 12; ++i) { p->Q[i] = Q[i]; p->R[i] = 1e-5; }
+    p->mu = 0.8; p->fz_min = 10.0; p->eps_abs = 1e-4; p->eps_rel = 1e-4; p->max_iter = 1000;
+    p->rho0 = 1e-4; p->sigma = 1e-6; p->alpha = 1.6; p->mode = 1; p->polish = 0;
+    p->check_termination = 10; p->adaptive_rho_interval = 25; p->pdas_max_iter = 16;
+}
+
+int emul_params_size() { return (int)sizeof(Params); }
+
+void emul_contact_table(int B, int N, const double* t0, double dt, double gait_hz, double duty,
+                        const double* off, uint64_t* mask) {
+    const int W = (4 * N + 63) / 64;
+    const double period = 1 / gait_hz;
+    for (int b = 0; b < B; ++b) {
+        for (int w = 0; w < W; ++w) mask[(size_t)b * W + w] = 0;
+        for (int leg = 0; leg < 4; ++leg)
+            for (int k = 0; k < N; ++k)
+                if (stance_bit(t0[b], dt, k, period, off[leg], duty)) {
+                    const int bit = leg * N + k;
+                    mask[(size_t)b * W + (bit >> 6)] |= (1ull << (bit & 63));
+                }
+    }
+}
+
+static QpIn make_in(int b, int N, const double* Ad, const double* Bd, const double* gd, const double* x0,
+                    const double* x_ref, const double* r_foot, const double* I_world, const double* mass,
+                    double dt, const uint64_t* mask) {
+    const int W = (4 * N + 63) / 64;
+    QpIn in;
+    in.Ad = Ad ? Ad + (size_t)b * 144 : nullptr;
+    in.Bd = Bd ? Bd + (size_t)b * N * 144 : nullptr;
+    in.gd = gd ? gd + (size_t)b * 12 : nullptr;
+    in.x0 = x0 + (size_t)b * 12;
+    in.x_ref = x_ref + (size_t)b * 12 * N;
+    in.r_foot = r_foot ? r_foot + (size_t)b * 12 * N : nullptr;
+    in.I_world = I_world ? I_world + (size_t)b * 9 : nullptr;
+    in.mass = mass ? mass[b] : 1.0;
+    in.dt = dt;
+    in.mask = mask ? mask + (size_t)b * W : nullptr;
+    in.N = N;
+    return in;
+}
+
+int emul_build(const Params* p, int B, int N, const double* Ad, const double* Bd, const double* gd,
+               const double* x0, const double* x_ref, const double* r_foot, const double* I_world,
+               const double* mass, double dt, double* H, double* g) {
+    const int nfmax = 4 * N, n = 12 * N;
+    Ws w;
+    std::vector<unsigned char> buf(ws_carve(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr) + 64);
+    ws_carve(w, buf.data(), N, nfmax, nullptr);
+    Cta c{0, 1, 0};
+    for (int b = 0; b < B; ++b) {
+        QpIn in = make_in(b, N, Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, nullptr);
+        build_dense_one(c, *p, in, w, nfmax, H + (size_t)b * n * n, g + (size_t)b * n);
+    }
+    return 0;
+}
+
+int emul_solve(const Params* p, int B, int N, int nfmax, const double* Ad, const double* Bd, const double* gd,
+               const double* x0, const double* x_ref, const double* r_foot, const double* I_world,
+               const double* mass, double dt, const uint64_t* mask, int warm, double* u, double* y, double* rho,
+               double* X, double* nu, int32_t* status, int32_t* iters, double* stats) {
+    Ws w;
+    std::vector<unsigned char> buf(ws_carve(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr) + 64);
+    ws_carve(w, buf.data(), N, nfmax, nullptr);
+    Cta c{0, 1, 0};
+    for (int b = 0; b < B; ++b) {
+        QpIn in = make_in(b, N, Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, mask);
+        QpOut o;
+        o.u = u + (size_t)b * 12 * N;
+        o.y = y + (size_t)b * 28 * N;
+        o.rho = rho ? rho + b : nullptr;
+        o.X = X ? X + (size_t)b * 12 * N : nullptr;
+        o.nu = nu ? nu + (size_t)b * 12 * N : nullptr;
+        o.status = status + b;
+        o.iters = iters + b;
+        o.stats = stats + (size_t)b * NSTAT;
+        solve_one(c, *p, in, o, w, nfmax, warm);
+    }
+    return 0;
+}
+
+size_t emul_ws_bytes(int N, int nfmax) {
+    Ws w;
+    return ws_carve(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr);
+}
+
+}  // extern "C"

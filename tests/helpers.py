@@ -1,0 +1,117 @@
+"""Shared test helpers: oracle QP construction from records, and the host emulation of the kernel
+source (tests/_emul) used by the CPU suite."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from oracle import condensed_qp, dynamics_ref, exact, gait_ref, sparse_qp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "_emul")
+EMUL_SRC = os.path.join(EMUL_DIR, "cmpc_emul.cpp")
+EMUL_LIB = os.path.join(EMUL_DIR, "libcmpc_emul.so")
+CORE = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh")
+
+PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])
+
+
+def oracle_inputs(rec, b):
+    """(contact, Ad, Bd, gd) of robot b by the oracle's restatement of the reference."""
+    ct = gait_ref.contact_table(rec.t0[b], rec.dt, rec.N, rec.gait_hz, rec.duty)
+    yaw = dynamics_ref.yaw_average(rec.x_ref[b])
+    Ac, Bc, gc = dynamics_ref.continuous_dynamics(rec.mass[b], rec.I_world[b], yaw, rec.r_foot[b])
+    Ad, Bd, gd = dynamics_ref.discrete_dynamics_closed(Ac, Bc, gc, rec.dt)
+    return ct, Ad, Bd, gd
+
+
+def oracle_solution(rec, b, contact=None):
+    ct, Ad, Bd, gd = oracle_inputs(rec, b)
+    if contact is not None:
+        ct = contact
+    cq = condensed_qp.build(Ad, Bd, gd, rec.x0[b], rec.x_ref[b], ct)
+    sol = exact.solve_exact(cq["H"], cq["g"], cq["A"], cq["l"], cq["u"])
+    return dict(ct=ct, Ad=Ad, Bd=Bd, gd=gd, cq=cq, sol=sol)
+
+
+def force_error(u, u_star):
+    """(abs inf-norm error in N, error relative to the 1e-2 N + 1e-3 rel tolerance of the north star)."""
+    d = np.abs(u - u_star)
+    tol = 1e-2 + 1e-3 * np.abs(u_star)
+    return d.max(), (d / tol).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# host emulation of csrc/cmpc_core.cuh (one-thread CTA)
+# ------------------------------------------------------------------------------------------------
+def build_emul():
+    stale = (not os.path.exists(EMUL_LIB) or
+             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE)))
+    if stale:
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", EMUL_LIB, EMUL_SRC], check=True)
+    return ctypes.CDLL(EMUL_LIB)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Emul:
+    def __init__(self):
+        self.lib = build_emul()
+        self.lib.emul_ws_bytes.restype = ctypes.c_size_t
+        self.psize = self.lib.emul_params_size()
+
+    def params(self, **kw):
+        buf = (ctypes.c_char * self.psize)()
+        self.lib.emul_default_params(buf)
+        d = np.frombuffer(buf, dtype=np.float64, count=31)
+        i = np.frombuffer(buf, dtype=np.int32, offset=31 * 8, count=6)
+        names_d = {"mu": 24, "fz_min": 25, "eps_abs": 26, "eps_rel": 27, "rho0": 28, "sigma": 29, "alpha": 30}
+        names_i = {"max_iter": 0, "mode": 1, "polish": 2, "check_termination": 3,
+                   "adaptive_rho_interval": 4, "pdas_max_iter": 5}
+        for k, v in kw.items():
+            if k in names_d:
+                d[names_d[k]] = v
+            else:
+                i[names_i[k]] = v
+        return buf
+
+    def contact_table(self, t0, dt, N, hz, duty, off=PHASE_OFFSET):
+        t0 = np.ascontiguousarray(t0, dtype=np.float64)
+        B = t0.shape[0]
+        mask = np.zeros((B, (4 * N + 63) // 64), np.uint64)
+        off = np.ascontiguousarray(off, dtype=np.float64)
+        self.lib.emul_contact_table(B, N, _p(t0), ctypes.c_double(dt), ctypes.c_double(hz), ctypes.c_double(duty),
+                                    _p(off), _p(mask))
+        return mask
+
+    def build(self, rec, Ad=None, Bd=None, gd=None, **kw):
+        B, N = rec.B, rec.N
+        n = 12 * N
+        H = np.zeros((B, n, n))
+        g = np.zeros((B, n))
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        Ad, Bd, gd = c(Ad), c(Bd), c(gd)
+        self.lib.emul_build(self.params(**kw), B, N, _p(Ad), _p(Bd), _p(gd), _p(rec.x0), _p(rec.x_ref),
+                            _p(rec.r_foot), _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(H), _p(g))
+        return H, g
+
+    def solve(self, rec, mask=None, nfmax=None, warm=0, state=None, Ad=None, Bd=None, gd=None, **kw):
+        B, N = rec.B, rec.N
+        nfmax = 4 * N if nfmax is None else nfmax
+        if mask is None:
+            mask = self.contact_table(rec.t0, rec.dt, N, rec.gait_hz, rec.duty)
+        if state is None:
+            u = np.zeros((B, 12 * N)); y = np.zeros((B, 28 * N)); rho = np.zeros(B)
+        else:
+            u, y, rho = state
+        X = np.zeros((B, 12 * N)); nu = np.zeros((B, 12 * N))
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); stats = np.zeros((B, 8))
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        Ad, Bd, gd = c(Ad), c(Bd), c(gd)
+        self.lib.emul_solve(self.params(**kw), B, N, nfmax, _p(Ad), _p(Bd), _p(gd), _p(rec.x0), _p(rec.x_ref),
+                            _p(rec.r_foot), _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
+                            _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats))
+        return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask)

@@ -1,0 +1,294 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / the drop-in class, against the
+oracle on the same seeded inputs.  Levels follow SURVEY.md section 8(c):
+  L0 bit-exact contact tables;  L1 A_d/B_d/g_d, H, g (<= 1e-12 rel);
+  L2 forces vs the exact optimum (1e-2 N abs + 1e-3 rel, the north-star tolerance);
+  L3 OSQP termination test at eps = 1e-5 on the reference's sparse QP.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from convex_mpc_b200 import records  # noqa: E402
+from helpers import force_error, oracle_inputs, oracle_solution  # noqa: E402
+from oracle import condensed_qp, gait_ref, sparse_qp  # noqa: E402
+
+TOL_ABS, TOL_REL = 1e-2, 1e-3      # BASELINE.json north_star: 1e-3 relative / 1e-2 N absolute
+
+
+@pytest.fixture(scope="module")
+def mod():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from convex_mpc_b200 import centroidal_mpc
+    return centroidal_mpc
+
+
+def make_mpc(mod, rec, **kw):
+    traj = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+    return mod.CentroidalMPC(None, traj, verbose=False, **kw), traj
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+def test_contact_table_bit_exact(mod, golden):
+    from convex_mpc_b200 import _lib
+    lib = _lib.load()
+    for ci in range(int(golden["ct_count"])):
+        hz, duty, N, dt = golden[f"ct{ci}_cfg"]
+        N = int(N)
+        t0 = golden[f"ct{ci}_t0"]
+        h = ctypes.c_void_p()
+        _lib.check(lib.cmpc_create(N, len(t0), 0, ctypes.byref(h)))
+        W = (4 * N + 63) // 64
+        mask = torch.zeros(len(t0), W, dtype=torch.int64, device="cuda")
+        _lib.check(lib.cmpc_contact_table(h, len(t0), dev(t0).data_ptr(), float(dt), float(hz), float(duty),
+                                          _lib.darr([0.5, 0, 0, 0.5]), mask.data_ptr(), None))
+        torch.cuda.synchronize()
+        got = gait_ref.unpack_mask(mask.cpu().numpy().view(np.uint64), N)
+        assert np.array_equal(got, golden[f"ct{ci}_table"]), f"contact table config {ci}"
+        lib.cmpc_destroy(h)
+
+
+def test_contact_table_bit_exact_large_random(mod):
+    from convex_mpc_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    B = 1 << 18
+    t0 = np.concatenate([1e-3 * rng.integers(0, 10 ** 6, B // 2), rng.uniform(0, 1000, B // 2)])
+    dt = (1 / 3) / 16
+    h = ctypes.c_void_p()
+    _lib.check(lib.cmpc_create(16, B, 0, ctypes.byref(h)))
+    mask = torch.zeros(B, 1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.cmpc_contact_table(h, B, dev(t0).data_ptr(), dt, 3.0, 0.6, _lib.darr([0.5, 0, 0, 0.5]),
+                                      mask.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = mask.cpu().numpy().view(np.uint64)
+    want = gait_ref.pack_mask(records.host_contact_table(t0, dt, 16, 3.0, 0.6))
+    assert np.array_equal(got, want)
+    # spot-check the vectorised host twin against the scalar oracle too
+    for i in range(0, B, 4099):
+        assert np.array_equal(gait_ref.unpack_mask(got[i], 16), gait_ref.contact_table(t0[i], dt, 16, 3.0, 0.6))
+    lib.cmpc_destroy(h)
+
+
+def test_dynamics_match_reference_golden(mod, golden):
+    from convex_mpc_b200 import _lib
+    lib = _lib.load()
+    for ci in range(int(golden["dyn_count"])):
+        N, dt, m = golden[f"dyn{ci}_in_scalar"]
+        N = int(N)
+        h = ctypes.c_void_p()
+        _lib.check(lib.cmpc_create(N, 1, 0, ctypes.byref(h)))
+        Ad = torch.zeros(1, 12, 12, dtype=torch.float64, device="cuda")
+        Bd = torch.zeros(1, N, 12, 12, dtype=torch.float64, device="cuda")
+        gd = torch.zeros(1, 12, dtype=torch.float64, device="cuda")
+        _lib.check(lib.cmpc_dynamics(h, 1, dev(golden[f"dyn{ci}_xref"]).data_ptr(),
+                                     dev(golden[f"dyn{ci}_rfoot"]).data_ptr(), dev(golden[f"dyn{ci}_I"]).data_ptr(),
+                                     dev(np.array([m])).data_ptr(), float(dt), Ad.data_ptr(), Bd.data_ptr(),
+                                     gd.data_ptr(), None))
+        torch.cuda.synchronize()
+        refB = golden[f"dyn{ci}_Bd"]
+        assert np.abs(Ad.cpu().numpy()[0] - golden[f"dyn{ci}_Ad"]).max() <= 1e-15
+        assert np.abs(Bd.cpu().numpy()[0] - refB).max() <= 1e-12 * max(1.0, np.abs(refB).max())
+        assert np.abs(gd.cpu().numpy()[0] - golden[f"dyn{ci}_gd"].reshape(12)).max() <= 1e-15
+        lib.cmpc_destroy(h)
+
+
+def test_build_H_g_match_oracle(mod):
+    from convex_mpc_b200 import _lib
+    lib = _lib.load()
+    rec = records.random_records(6, seed=21)
+    B, N = rec.B, rec.N
+    n = 12 * N
+    h = ctypes.c_void_p()
+    _lib.check(lib.cmpc_create(N, B, 0, ctypes.byref(h)))
+    H = torch.zeros(B, n, n, dtype=torch.float64, device="cuda")
+    g = torch.zeros(B, n, dtype=torch.float64, device="cuda")
+    x0, xr, rf, I, m = dev(rec.x0), dev(rec.x_ref), dev(rec.r_foot), dev(rec.I_world), dev(rec.mass)
+    _lib.check(lib.cmpc_build(h, B, None, None, None, x0.data_ptr(), xr.data_ptr(), rf.data_ptr(), I.data_ptr(),
+                              m.data_ptr(), rec.dt, H.data_ptr(), g.data_ptr(), None))
+    AB = [oracle_inputs(rec, b) for b in range(B)]
+    Ad = dev(np.stack([a[1] for a in AB])); Bd = dev(np.stack([a[2] for a in AB]))
+    gd = dev(np.stack([a[3].reshape(12) for a in AB]))
+    H2 = torch.zeros_like(H); g2 = torch.zeros_like(g)
+    _lib.check(lib.cmpc_build(h, B, Ad.data_ptr(), Bd.data_ptr(), gd.data_ptr(), x0.data_ptr(), xr.data_ptr(),
+                              None, None, None, rec.dt, H2.data_ptr(), g2.data_ptr(), None))
+    torch.cuda.synchronize()
+    Hn, gn, H2n, g2n = H.cpu().numpy(), g.cpu().numpy(), H2.cpu().numpy(), g2.cpu().numpy()
+    for b in range(B):
+        cq = condensed_qp.build(AB[b][1], AB[b][2], AB[b][3], rec.x0[b], rec.x_ref[b], np.ones((4, N), dtype=int))
+        for Hx, gx in ((Hn[b], gn[b]), (H2n[b], g2n[b])):
+            assert np.abs(Hx - cq["H"]).max() <= 1e-12 * np.abs(cq["H"]).max()
+            assert np.abs(gx - cq["g"]).max() <= 1e-11 * np.abs(cq["g"]).max()
+            assert np.array_equal(Hx, Hx.T)
+    lib.cmpc_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stress,B", [(0.0, 96), (0.5, 96), (1.0, 64)])
+def test_forces_match_exact_optimum(mod, stress, B):
+    rec = records.random_records(B, seed=500 + int(10 * stress), stress=stress)
+    mpc, traj = make_mpc(mod, rec)
+    sol = mpc.solve_QP(None, traj)
+    u = sol["u"].cpu().numpy()                       # (B,12,N)
+    w = sol["x"].full()                              # (B,24N)
+    status = sol["status"].cpu().numpy()
+    stats = sol["stats"].cpu().numpy()
+    assert (status == 1).all()
+    N = rec.N
+    worst = 0.0
+    for b in range(B):
+        o = oracle_solution(rec, b)
+        assert o["sol"]["ok"]
+        U = u[b].reshape(-1, order="F")              # back to w[12N:] order
+        assert np.array_equal(U, w[b, 12 * N:])
+        d = np.abs(U - o["sol"]["U"])
+        assert (d <= TOL_ABS + TOL_REL * np.abs(o["sol"]["U"])).all(), (b, d.max())
+        worst = max(worst, d.max())
+        # L3: the lifted point passes OSQP's own termination test at eps = 1e-5 on the reference's QP
+        sq = sparse_qp.build(o["Ad"], o["Bd"], o["gd"], rec.x0[b], rec.x_ref[b], o["ct"])
+        lam_x = sol["lam_x"].full()[b]
+        lam_a = sol["lam_a"].full()[b]
+        eps = 1e-5
+        P, q, A, l, uu = sparse_qp.as_osqp_form(sq)
+        y = np.concatenate([lam_x, lam_a])
+        Ax = A @ w[b]
+        z = np.clip(Ax, l, uu)
+        r_p = np.abs(Ax - z).max()
+        r_d = np.abs(P @ w[b] + q + A.T @ y).max()
+        assert r_p <= eps + eps * max(np.abs(Ax).max(), np.abs(z).max())
+        assert r_d <= eps + eps * max(np.abs(P @ w[b]).max(), np.abs(A.T @ y).max(), np.abs(q).max())
+        assert abs(sparse_qp.objective(sq, w[b]) - stats[b, 2]) <= 1e-8 * max(1.0, abs(stats[b, 2]))
+    assert worst < 1e-6        # in practice the active-set path is exact to ~1e-9 N
+
+
+def test_drop_in_single_robot_api(mod):
+    """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
+    rec = records.random_records(1, seed=9, stress=1.0)
+    ct, Ad, Bd, gd = oracle_inputs(rec, 0)
+
+    class Traj:       # what ComTraj exposes, reference shapes
+        N = rec.N
+        initial_x_vec = rec.x0[0].reshape(12, 1)
+        contact_table = ct
+        def compute_x_ref_vec(self):
+            return rec.x_ref[0]
+    traj = Traj()
+    traj.Ad, traj.Bd, traj.gd = Ad, Bd, gd
+    mpc = mod.CentroidalMPC(None, traj, verbose=False)
+    sol = mpc.solve_QP(None, traj, False)
+    w_opt = sol["x"].full().flatten()
+    N = traj.N
+    assert w_opt.shape == (24 * N,)
+    X_opt = w_opt[:12 * N].reshape((12, N), order="F")
+    U_opt = w_opt[12 * N:].reshape((12, N), order="F")
+    o = oracle_solution(rec, 0)
+    assert force_error(U_opt.reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+    assert np.abs(X_opt.reshape(-1, order="F") - condensed_qp.rollout(o["cq"], o["sol"]["U"])).max() < 1e-8
+    assert mpc.solve_time > 0 and mpc.update_time > 0
+    assert sol["lam_x"].full().shape == (24 * N, 1) and sol["lam_a"].full().shape == (28 * N, 1)
+    assert tuple(sol["u"].shape) == (12, N)
+    # second call warm-starts from the first (centroidal_mpc.py:92-95) and returns the same optimum
+    sol2 = mpc.solve_QP(None, traj, False)
+    assert np.abs(sol2["x"].full().flatten() - w_opt).max() < 1e-7
+
+
+def test_AdBd_path_equals_device_dynamics_path(mod):
+    rec = records.random_records(32, seed=77, stress=0.5)
+    mpc, traj = make_mpc(mod, rec)
+    a = mpc.solve_QP(None, traj)["u"].cpu().numpy()
+    AB = [oracle_inputs(rec, b) for b in range(rec.B)]
+    traj2 = mod.BatchedComTraj(rec.N, dev(rec.x0), dev(rec.x_ref), rec.dt, Ad=dev(np.stack([x[1] for x in AB])),
+                               Bd=dev(np.stack([x[2] for x in AB])), gd=dev(np.stack([x[3].reshape(12) for x in AB])),
+                               contact_table=dev(np.stack([x[0] for x in AB])))
+    mpc2 = mod.CentroidalMPC(None, traj2, verbose=False)
+    b = mpc2.solve_QP(None, traj2)["u"].cpu().numpy()
+    assert np.abs(a - b).max() < 1e-6
+
+
+def test_admm_mode_and_polish(mod):
+    rec = records.random_records(32, seed=31, stress=0.3)
+    mpc, traj = make_mpc(mod, rec, mode="admm", eps_abs=1e-5, eps_rel=1e-5, max_iter=4000)
+    sol = mpc.solve_QP(None, traj)
+    st = sol["stats"].cpu().numpy()
+    assert (sol["status"].cpu().numpy() == 1).all() and (sol["iters"].cpu().numpy() > 0).all()
+    assert (st[:, 7] == 2).all()
+    u_admm = sol["u"].cpu().numpy()
+    mpc2, _ = make_mpc(mod, rec, mode="admm", polish=True)
+    u_pol = mpc2.solve_QP(None, traj)["u"].cpu().numpy()
+    for b in range(rec.B):
+        U = oracle_solution(rec, b)["sol"]["U"]
+        assert np.abs(u_admm[b].reshape(-1, order="F") - U).max() < 2.0      # OSQP-like: loose in flat directions
+        assert force_error(u_pol[b].reshape(-1, order="F"), U)[1] < 1.0
+
+
+def test_edge_cases(mod):
+    rec = records.random_records(8, seed=41, stress=0.5)
+    N = rec.N
+    for val, nfree in ((0, 0), (1, 12 * N)):
+        traj = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+        traj.contact_table = torch.full((rec.B, 4, N), val, dtype=torch.int32, device="cuda")
+        mpc = mod.CentroidalMPC(None, traj, verbose=False)
+        sol = mpc.solve_QP(None, traj)
+        st = sol["stats"].cpu().numpy()
+        assert (sol["status"].cpu().numpy() == 1).all() and (st[:, 3] == nfree).all()
+        u = sol["u"].cpu().numpy()
+        for b in range(3):
+            o = oracle_solution(rec, b, contact=np.full((4, N), val))
+            assert force_error(u[b].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+    # B = 1 batched, and a stance bound that is too small is reported per robot
+    one = rec.slice(0, 1)
+    mpc, traj = make_mpc(mod, one)
+    assert tuple(mpc.solve_QP(None, traj)["u"].shape) == (1, 12, N)
+    mpc, traj = make_mpc(mod, rec, max_stance=8)
+    assert (mpc.solve_QP(None, traj)["status"].cpu().numpy() == -20).all()
+
+
+def test_host_entry_matches_device_entry(mod):
+    rec = records.random_records(3000, seed=88, stress=0.2)
+    mpc, traj = make_mpc(mod, rec)
+    a = mpc.solve_QP(None, traj)["x"].full()[:, 12 * rec.N:]
+    u, st, it = mpc.solve_host(rec.x0, rec.x_ref, rec.r_foot, rec.I_world, rec.mass, rec.t0, rec.dt, rec.gait_hz, rec.duty)
+    assert (st.numpy() == 1).all()
+    assert np.abs(u.numpy() - a).max() < 1e-9
+
+
+def test_full_size_properties(mod):
+    """BASELINE config #3 at full size (65 536 robots): every QP certified by its own KKT residuals
+    (computed in-kernel from the roll-out and co-states, independent of the factorisation)."""
+    rec = records.random_records(65536, seed=65536)
+    mpc, traj = make_mpc(mod, rec, max_stance=40)
+    sol = mpc.solve_QP(None, traj)
+    st = sol["stats"].cpu().numpy()
+    status = sol["status"].cpu().numpy()
+    assert (status == 1).all()
+    assert st[:, 0].max() < 1e-8 and st[:, 1].max() < 1e-8
+    u = sol["u"]
+    # swing legs carry exactly zero force; stance legs respect fz >= 10 and the pyramid
+    ct = torch.from_numpy(records.host_contact_table(rec.t0, rec.dt, rec.N, rec.gait_hz, rec.duty)).cuda()
+    f = u.reshape(rec.B, 4, 3, rec.N)
+    swing = (ct == 0)
+    assert float(f.abs().amax(dim=2)[swing].max()) == 0.0
+    fz = f[:, :, 2, :][~swing]
+    assert float(fz.min()) >= 10.0 - 1e-8
+    assert float((f[:, :, 0, :].abs()[~swing] - 0.8 * fz).max()) <= 1e-8
+    assert float((f[:, :, 1, :].abs()[~swing] - 0.8 * fz).max()) <= 1e-8
+    # total vertical force at the first step ~ weight (sanity of the whole pipeline)
+    fz0 = f[:, :, 2, 0].sum(dim=1)
+    assert 0.3 * 15.02 * 9.81 < float(fz0.median()) < 3.0 * 15.02 * 9.81
+    # idempotence: a warm-started second solve returns the same forces
+    u1 = u.clone()
+    u2 = mpc.solve_QP(None, traj)["u"]
+    assert float((u1 - u2).abs().max()) < 1e-6
+    # sampled L2 check against the oracle
+    un = u1.cpu().numpy()
+    for b in range(0, rec.B, 2048):
+        o = oracle_solution(rec, b)
+        assert force_error(un[b].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3

@@ -1,0 +1,115 @@
+"""CPU check of the *kernel source* (csrc/cmpc_core.cuh compiled for the host with a one-thread CTA,
+tests/_emul) against the oracle.  Races and launch plumbing are only visible on the GPU (-m gpu), but
+indexing, recursions and the solver control flow are identical code."""
+import numpy as np
+import pytest
+
+from convex_mpc_b200 import records
+from helpers import Emul, force_error, oracle_inputs, oracle_solution
+from oracle import condensed_qp, gait_ref, sparse_qp
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return Emul()
+
+
+def test_contact_table_bit_exact_vs_golden(emul, golden):
+    for ci in range(int(golden["ct_count"])):
+        hz, duty, N, dt = golden[f"ct{ci}_cfg"]
+        N = int(N)
+        if N > 48:
+            continue
+        mask = emul.contact_table(golden[f"ct{ci}_t0"], float(dt), N, float(hz), float(duty))
+        got = gait_ref.unpack_mask(mask, N)
+        assert np.array_equal(got, golden[f"ct{ci}_table"]), ci
+
+
+def test_contact_table_bit_exact_random(emul):
+    rng = np.random.default_rng(5)
+    t0 = np.concatenate([1e-3 * rng.integers(0, 100000, 20000), rng.uniform(0, 50, 20000)])
+    dt = (1 / 3) / 16
+    mask = emul.contact_table(t0, dt, 16, 3, 0.6)
+    got = gait_ref.unpack_mask(mask, 16)
+    for i in range(0, t0.size, 97):
+        assert np.array_equal(got[i], gait_ref.contact_table(t0[i], dt, 16, 3, 0.6))
+
+
+def test_dense_build_matches_oracle(emul):
+    rec = records.random_records(4, seed=21)
+    H, g = emul.build(rec)
+    for b in range(rec.B):
+        ct, Ad, Bd, gd = oracle_inputs(rec, b)
+        cq = condensed_qp.build(Ad, Bd, gd, rec.x0[b], rec.x_ref[b], np.ones((4, rec.N), dtype=int))
+        scale = np.abs(cq["H"]).max()
+        assert np.abs(H[b] - cq["H"]).max() <= 1e-12 * scale
+        assert np.abs(g[b] - cq["g"]).max() <= 1e-12 * np.abs(cq["g"]).max()
+    # drop-in path: the same data handed over as (Ad, Bd, gd)
+    AB = [oracle_inputs(rec, b) for b in range(rec.B)]
+    H2, g2 = emul.build(rec, Ad=np.stack([a[1] for a in AB]), Bd=np.stack([a[2] for a in AB]),
+                        gd=np.stack([a[3].reshape(12) for a in AB]))
+    assert np.abs(H2 - H).max() <= 1e-12 * np.abs(H).max()
+    assert np.abs(g2 - g).max() <= 1e-11 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("stress", [0.0, 0.5, 1.0])
+def test_forces_match_exact_optimum(emul, stress):
+    rec = records.random_records(24, seed=100 + int(10 * stress), stress=stress)
+    r = emul.solve(rec)
+    assert (r["status"] == 1).all()
+    for b in range(rec.B):
+        o = oracle_solution(rec, b)
+        assert o["sol"]["ok"]
+        assert np.array_equal(gait_ref.unpack_mask(r["mask"][b], rec.N), o["ct"])
+        err, rel = force_error(r["u"][b], o["sol"]["U"])
+        assert rel < 1e-3, (b, err)            # 1000x inside the 1e-2 N / 1e-3 tolerance
+        assert np.abs(r["y"][b] - o["sol"]["y"]).max() < 1e-7
+        # lifted solution and cost in the reference's own (sparse) form
+        sq = sparse_qp.build(o["Ad"], o["Bd"], o["gd"], rec.x0[b], rec.x_ref[b], o["ct"])
+        w = np.concatenate([r["X"][b], r["u"][b]])
+        assert abs(sparse_qp.objective(sq, w) - r["stats"][b, 2]) <= 1e-9 * max(1, abs(r["stats"][b, 2]))
+        Aw = sq["A"] @ w
+        assert np.abs(Aw[:12 * rec.N] - sq["lba"][:12 * rec.N]).max() < 1e-10
+        lam_x = np.concatenate([np.zeros(12 * rec.N), r["y"][b][:12 * rec.N]])
+        lam_a = np.concatenate([r["nu"][b], r["y"][b][12 * rec.N:]])
+        assert np.abs(sq["H"] @ w + sq["g"] + lam_x + sq["A"].T @ lam_a).max() < 1e-8
+
+
+def test_admm_mode_is_osqp_like(emul):
+    """mode 0 = plain ADMM with OSQP's termination rule: residuals below eps, forces only roughly right
+    (that is how OSQP itself behaves on this flat QP)."""
+    rec = records.random_records(8, seed=31, stress=0.3)
+    r = emul.solve(rec, mode=0, eps_abs=1e-6, eps_rel=1e-6, max_iter=4000)
+    assert (r["status"] == 1).all() and (r["iters"] > 0).all()
+    for b in range(rec.B):
+        o = oracle_solution(rec, b)
+        assert np.abs(r["u"][b] - o["sol"]["U"]).max() < 0.2
+        assert r["stats"][b, 0] < 1e-3 and r["stats"][b, 1] < 1e-4
+    # polish on top of ADMM recovers the exact optimum
+    r2 = emul.solve(rec, mode=0, polish=1, eps_abs=1e-4, eps_rel=1e-4)
+    for b in range(rec.B):
+        o = oracle_solution(rec, b)
+        assert force_error(r2["u"][b], o["sol"]["U"])[1] < 1e-3
+
+
+def test_warm_start_and_edge_masks(emul):
+    rec = records.random_records(6, seed=41, stress=0.5)
+    cold = emul.solve(rec)
+    warm = emul.solve(rec, warm=1, state=(cold["u"].copy(), cold["y"].copy(), cold["rho"].copy()))
+    assert np.abs(warm["u"] - cold["u"]).max() < 1e-7
+    assert (warm["stats"][:, 6] <= np.maximum(cold["stats"][:, 6], 1)).all()
+    N = rec.N
+    W = 1
+    # all swing: zero forces, multipliers close stationarity; all stance: 192 free variables
+    for bits, nfree in ((0, 0), (2 ** 64 - 1, 192)):
+        mask = np.full((rec.B, W), bits, dtype=np.uint64)
+        r = emul.solve(rec, mask=mask)
+        assert (r["status"] == 1).all() and (r["stats"][:, 3] == nfree).all()
+        ct = np.full((4, N), 1 if bits else 0)
+        for b in range(2):
+            o = oracle_solution(rec, b, contact=ct)
+            assert force_error(r["u"][b], o["sol"]["U"])[1] < 1e-3
+            assert np.abs(r["y"][b] - o["sol"]["y"]).max() < 1e-7
+    # a bound on stance foot-steps that is too small is reported, never silently truncated
+    r = emul.solve(rec, nfmax=8)
+    assert (r["status"] == -20).all()
