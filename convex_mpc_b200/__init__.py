@@ -15,6 +15,7 @@ def __getattr__(name):
     # and build tooling work on machines without a GPU
     if name in ("CentroidalMPC", "BatchedComTraj", "MPCSolution", "COST_MATRIX_Q", "COST_MATRIX_R", "MU", "NX", "NU",
                 "OPTS", "SOLVER_NAME", "centroidal_mpc"):
-        from . import centroidal_mpc as _m
+        import importlib
+        _m = importlib.import_module(__name__ + ".centroidal_mpc")
         return _m if name == "centroidal_mpc" else getattr(_m, name)
     raise AttributeError(name)

@@ -48,7 +48,8 @@ def test_contact_table_bit_exact(mod, golden):
         _lib.check(lib.cmpc_create(N, len(t0), 0, ctypes.byref(h)))
         W = (4 * N + 63) // 64
         mask = torch.zeros(len(t0), W, dtype=torch.int64, device="cuda")
-        _lib.check(lib.cmpc_contact_table(h, len(t0), dev(t0).data_ptr(), float(dt), float(hz), float(duty),
+        t0_d = dev(t0)          # keep device inputs referenced until the kernel has run
+        _lib.check(lib.cmpc_contact_table(h, len(t0), t0_d.data_ptr(), float(dt), float(hz), float(duty),
                                           _lib.darr([0.5, 0, 0, 0.5]), mask.data_ptr(), None))
         torch.cuda.synchronize()
         got = gait_ref.unpack_mask(mask.cpu().numpy().view(np.uint64), N)
@@ -66,7 +67,8 @@ def test_contact_table_bit_exact_large_random(mod):
     h = ctypes.c_void_p()
     _lib.check(lib.cmpc_create(16, B, 0, ctypes.byref(h)))
     mask = torch.zeros(B, 1, dtype=torch.int64, device="cuda")
-    _lib.check(lib.cmpc_contact_table(h, B, dev(t0).data_ptr(), dt, 3.0, 0.6, _lib.darr([0.5, 0, 0, 0.5]),
+    t0_d = dev(t0)
+    _lib.check(lib.cmpc_contact_table(h, B, t0_d.data_ptr(), dt, 3.0, 0.6, _lib.darr([0.5, 0, 0, 0.5]),
                                       mask.data_ptr(), None))
     torch.cuda.synchronize()
     got = mask.cpu().numpy().view(np.uint64)
@@ -89,10 +91,10 @@ def test_dynamics_match_reference_golden(mod, golden):
         Ad = torch.zeros(1, 12, 12, dtype=torch.float64, device="cuda")
         Bd = torch.zeros(1, N, 12, 12, dtype=torch.float64, device="cuda")
         gd = torch.zeros(1, 12, dtype=torch.float64, device="cuda")
-        _lib.check(lib.cmpc_dynamics(h, 1, dev(golden[f"dyn{ci}_xref"]).data_ptr(),
-                                     dev(golden[f"dyn{ci}_rfoot"]).data_ptr(), dev(golden[f"dyn{ci}_I"]).data_ptr(),
-                                     dev(np.array([m])).data_ptr(), float(dt), Ad.data_ptr(), Bd.data_ptr(),
-                                     gd.data_ptr(), None))
+        xr, rf, Iw, ms = (dev(golden[f"dyn{ci}_xref"]), dev(golden[f"dyn{ci}_rfoot"]), dev(golden[f"dyn{ci}_I"]),
+                          dev(np.array([m])))
+        _lib.check(lib.cmpc_dynamics(h, 1, xr.data_ptr(), rf.data_ptr(), Iw.data_ptr(), ms.data_ptr(), float(dt),
+                                     Ad.data_ptr(), Bd.data_ptr(), gd.data_ptr(), None))
         torch.cuda.synchronize()
         refB = golden[f"dyn{ci}_Bd"]
         assert np.abs(Ad.cpu().numpy()[0] - golden[f"dyn{ci}_Ad"]).max() <= 1e-15
