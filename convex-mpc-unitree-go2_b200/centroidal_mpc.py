@@ -176,6 +176,10 @@ class CentroidalMPC:
             check(self._lib.cmpc_set_max_stance(self._h, int(max_stance)))
         self._state_B = None
         self._warm = False
+        self._warm_host = 0
+        self.kernel_ms = 0.0
+        with torch.cuda.device(self.device):
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         self.x_prev = self.lam_x_prev = self.lam_a_prev = None
         self.last_stats = None
         if verbose:
@@ -210,6 +214,7 @@ class CentroidalMPC:
     def reset(self):
         """Forget the warm-start state (the reference has no such call: it warm-starts forever)."""
         self._warm = False
+        self._warm_host = 0
         self.x_prev = self.lam_x_prev = self.lam_a_prev = None
 
     # ------------------------------------------------------------------------------------------
@@ -322,13 +327,16 @@ class CentroidalMPC:
             torch.cuda.current_stream().synchronize()
             t1 = time.perf_counter()
             p = lambda k: t[k].data_ptr() if k in t else None
+            self._ev[0].record()
             check(self._lib.cmpc_solve(
                 self._h, B, p("Ad"), p("Bd"), p("gd"), p("x0"), p("x_ref"), p("r_foot"), p("I_world"), p("mass"),
                 float(t.get("dt", 0.0)), self._mask.data_ptr(), int(self._warm),
                 self._u.data_ptr(), self._y.data_ptr(), self._rho.data_ptr(), self._X.data_ptr(),
                 self._nu.data_ptr(), self._status.data_ptr(), self._iters.data_ptr(), self._stats.data_ptr(),
                 stream))
+            self._ev[1].record()
             torch.cuda.current_stream().synchronize()   # the reference call is blocking (centroidal_mpc.py:98)
+            self.kernel_ms = self._ev[0].elapsed_time(self._ev[1])     # device time of the fused solve kernel
         t2 = time.perf_counter()
         self.update_time = (t1 - t0) * 1e3      # ms, as centroidal_mpc.py:102-105
         self.solve_time = (t2 - t1) * 1e3
@@ -387,7 +395,7 @@ class CentroidalMPC:
         check(self._lib.cmpc_solve_host(
             self._h, B, host_ptr(x0, B * 12), host_ptr(x_ref, B * 12 * N), host_ptr(r_foot, B * 12 * N),
             host_ptr(I_world, B * 9), host_ptr(mass, B), host_ptr(t0, B), float(dt), float(gait_hz), float(duty),
-            _lib.darr(phase_offset), int(self._warm_host if hasattr(self, "_warm_host") else 0),
+            _lib.darr(phase_offset), int(self._warm_host),
             u.data_ptr(), st.data_ptr(), it.data_ptr()))
         self._warm_host = 1 if OPTS.get("warm_start_primal", True) else 0
         return u, st, it

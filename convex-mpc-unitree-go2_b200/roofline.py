@@ -1,0 +1,46 @@
+"""Algorithmic work of the fused solve kernel per QP, used for the roofline
+fraction that ``bench.py`` reports.  "Algorithmic" = the flops the mathematics needs for the route
+each QP actually took (its number of free variables n, active-set solves, ADMM iterations and
+factorisations come from the kernel's own per-QP statistics) -- not the instructions executed.
+
+    build        0.4e6 * (n/192)^2      closed-form condensed H, g   
+    cholesky     n^3 / 3
+    tri-solves   2 n^2                  forward + backward substitution for the unconstrained minimiser
+    inverse      n^3 / 3                W = L^-1, only when an active-set / ADMM phase runs
+    active set   per working-set solve with k active rows:  k^2 n + k^3/3 + 2 n^2
+    ADMM         per iteration 2 n^2 + 12 (n + m), m = 5n/3;  per re-factorisation  build + 2 n^3 / 3
+    epilogue     roll-out + co-states + residuals: 2 * (2*144*N + 2*12*n) + 4 n
+
+Bytes: every QP reads 3 280 B of inputs and writes u, y, X, nu, status, iters, stats
+(8*(12N + 28N + 12N + 12N) + 8 + 64 B) -- H never leaves the SM.
+"""
+import numpy as np
+
+
+def flops_per_qp(n, path, as_iters, n_active, admm_iters, nfac, N=16):
+    n = np.asarray(n, dtype=np.float64)
+    path = np.asarray(path)
+    k = np.asarray(n_active, dtype=np.float64)
+    build = 0.4e6 * (n / 192.0) ** 2
+    f = build + n ** 3 / 3 + 2 * n ** 2
+    f = f + 2 * (2 * 144 * N + 24 * n) + 4 * n
+    needs_inv = path != 0
+    f = f + needs_inv * (n ** 3 / 3)
+    f = f + np.asarray(as_iters, dtype=np.float64) * (k ** 2 * n + k ** 3 / 3 + 2 * n ** 2)
+    m = 5.0 * n / 3.0
+    f = f + np.asarray(admm_iters, dtype=np.float64) * (2 * n ** 2 + 12 * (n + m))
+    f = f + np.asarray(nfac, dtype=np.float64) * (build + 2 * n ** 3 / 3)
+    return f
+
+
+def batch_flops(stats, iters, N=16):
+    """Total algorithmic flops of a batch from the (B, NSTAT) stats array and the ADMM iteration counts."""
+    stats = np.asarray(stats)
+    path = stats[:, 7].astype(np.int64)
+    admm = (path >= 2)
+    return float(flops_per_qp(stats[:, 3], path, stats[:, 6], stats[:, 4], np.asarray(iters) * admm,
+                              admm.astype(np.float64), N).sum())
+
+
+def bytes_per_qp(N=16):
+    return 8 * (12 + 12 * N + 12 * N + 9 + 1 + 1) + 8 + 8 * (12 * N + 28 * N + 12 * N + 12 * N) + 8 + 64
