@@ -23,6 +23,7 @@ PROTOTYPES = {
     "cmpc_set_params": (c_int, [c_void_p, c_dp, c_dp, c_double, c_double, c_double, c_double, c_int,
                                 c_double, c_double, c_double, c_int, c_int, c_int, c_int]),
     "cmpc_set_max_stance": (c_int, [c_void_p, c_int]),
+    "cmpc_set_generic": (c_int, [c_void_p, c_int]),
     "cmpc_contact_table": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, c_double, c_dp,
                                    c_void_p, c_void_p]),
     "cmpc_pack_contact": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -36,6 +37,7 @@ PROTOTYPES = {
     "cmpc_host_stats": (c_int, [c_void_p, c_int, c_void_p]),
     "cmpc_launch_count": (ctypes.c_longlong, []),
     "cmpc_microbench": (c_int, [c_int, c_dp, c_dp]),
+    "cmpc_microbench_dmma": (c_int, [c_int, c_dp, c_dp]),
     "cmpc_last_error": (ctypes.c_char_p, []),
     "cmpc_version": (ctypes.c_char_p, []),
 }

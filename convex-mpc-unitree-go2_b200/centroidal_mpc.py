@@ -138,12 +138,14 @@ class CentroidalMPC:
                   from ``traj.m, I_com_world, r_*_foot_world``; "traj" / "device" force one
       eps_abs, eps_rel, max_iter, polish, check_termination, adaptive_rho_interval, rho0, sigma, alpha
       max_stance  upper bound on stance foot-steps per robot (see cmpc_set_max_stance)
+      generic_kernel  diagnostics: solve raw-input batches with the generic kernel (the one that serves
+                  caller-supplied Ad/Bd/gd) instead of the closed-form fast kernel
     """
 
     def __init__(self, go2, traj, *, device=None, mode="active_set", dynamics="auto", max_batch=None,
                  eps_abs=None, eps_rel=None, max_iter=None, polish=None, check_termination=None,
                  adaptive_rho_interval=None, rho0=1e-4, sigma=1e-6, alpha=1.6, mu=MU, fz_min=FZ_MIN,
-                 Q=None, R=None, max_stance=None, verbose=True):
+                 Q=None, R=None, max_stance=None, generic_kernel=False, verbose=True):
         if not torch.cuda.is_available():
             raise _lib.CmpcError("CentroidalMPC needs a CUDA device (no CPU fallback)")
         self._lib = _lib.load()
@@ -174,6 +176,8 @@ class CentroidalMPC:
         self._push_params()
         if max_stance is not None:
             check(self._lib.cmpc_set_max_stance(self._h, int(max_stance)))
+        if generic_kernel:
+            check(self._lib.cmpc_set_generic(self._h, 1))
         self._state_B = None
         self._warm = False
         self._warm_host = 0

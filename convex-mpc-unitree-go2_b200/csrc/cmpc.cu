@@ -17,6 +17,7 @@
 
 #include "../../include/cmpc.h"
 #include "cmpc_core.cuh"
+#include "cmpc_fast.cuh"
 
 using namespace cmpc;
 
@@ -158,6 +159,32 @@ solve_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, doub
     }
 }
 
+// v2 fast path (raw inputs): persistent-style grid-stride loop, one CTA per robot at a time,
+// two CTAs resident per SM when the workspace allows it.
+__global__ void __launch_bounds__(kThreads, 2)
+solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hb_scratch, size_t hb_stride) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    fast::WsF w;
+    fast::ws_carve_fast(w, smem, bi.N, nfmax, hb_scratch ? hb_scratch + (size_t)blockIdx.x * hb_stride : nullptr);
+    const fast::Cx c = fast::make_cx(threadIdx.x, blockDim.x);
+    fast::init_tables(c, w);
+    const int N = bi.N;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        QpIn in = qp_in(bi, b);
+        QpOut o;
+        o.u = bo.u + (size_t)b * 12 * N;
+        o.y = bo.y + (size_t)b * 28 * N;
+        o.rho = bo.rho ? bo.rho + b : nullptr;
+        o.X = bo.X ? bo.X + (size_t)b * 12 * N : nullptr;
+        o.nu = bo.nu ? bo.nu + (size_t)b * 12 * N : nullptr;
+        o.status = bo.status + b;
+        o.iters = bo.iters + b;
+        o.stats = bo.stats + (size_t)b * NSTAT;
+        fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Roofline denominators: dependent-free DFMA streams and shared-memory 8-byte reads.
 // ---------------------------------------------------------------------------------------------
@@ -190,6 +217,37 @@ __global__ void smem_peak_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// FP64 tensor-core (DMMA m8n8k4) stream: 8 independent accumulator pairs per warp.
+__global__ void dmma_peak_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3 + i; c[i][1] = 1.0 + i; }
+    const double a = 1.0000001, b = 0.9999999;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// dependent DMMA chain: latency of one m8n8k4 in cycles (single warp)
+__global__ void dmma_latency_kernel(double* out, long long* cycles, int iters) {
+    double c0 = threadIdx.x, c1 = 1.0;
+    const double a = 1.0000001, b = 0.9999999;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    const long long t1 = clock64();
+    out[threadIdx.x] = c0 + c1;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -198,8 +256,9 @@ __global__ void smem_peak_kernel(double* out, int iters) {
 struct cmpc_handle {
     int N = 16, W = 1, max_batch = 0, device = 0;
     int nfmax = 64;        // largest number of stance foot-steps any robot may have
+    int force_generic = 0; // diagnostics: route raw inputs through the generic kernel too
     int sm_count = 148;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     Params p;
     double* hp_scratch = nullptr;   // packed-matrix scratch when it does not fit shared memory
     size_t hp_stride = 0;
@@ -265,6 +324,45 @@ int plan_launch(cmpc_handle* h, int nfmax, const void* kernel, size_t* smem_out,
     return 0;
 }
 
+size_t smem_needed_fast(int N, int nfmax, bool hb_external) {
+    fast::WsF w;
+    unsigned char* base = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20));
+    static double dummy;
+    return fast::ws_carve_fast(w, base, N, nfmax, hb_external ? &dummy : nullptr);
+}
+
+// Fast path: where the block-packed matrix lives, shared-memory bytes, and the grid.
+int plan_launch_fast(cmpc_handle* h, int nfmax, int B, size_t* smem_out, double** hb, size_t* stride, int* grid) {
+    size_t need = smem_needed_fast(h->N, nfmax, false);
+    *hb = nullptr; *stride = 0;
+    int per_sm = 1;
+    if (need > h->smem_optin) {
+        need = smem_needed_fast(h->N, nfmax, true);
+        if (need > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
+        const size_t nblk = (3 * (size_t)nfmax + 7) / 8;
+        const size_t st = nblk * (nblk + 1) / 2 * 64;
+        const int ctas = h->sm_count * 2;
+        if (h->hp_stride < st || h->hp_ctas < ctas) {
+            if (h->hp_scratch) cudaFree(h->hp_scratch);
+            h->hp_scratch = nullptr;
+            CU_TRY(cudaMalloc(&h->hp_scratch, st * ctas * sizeof(double)));
+            h->hp_stride = st; h->hp_ctas = ctas;
+        }
+        *hb = h->hp_scratch; *stride = h->hp_stride;
+        per_sm = 2;
+    } else {
+        // CTAs per SM by shared memory (1 KB per CTA is reserved by the system)
+        per_sm = (int)(h->smem_per_sm / (need + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 2) per_sm = 2;      // register file: 256 threads x 128 registers x 2
+    }
+    CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    *smem_out = need;
+    const int cap = h->sm_count * per_sm;
+    *grid = B < cap ? B : cap;
+    return 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -290,6 +388,8 @@ int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
     h->sm_count = v;
     CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     h->smem_optin = (size_t)v;
+    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    h->smem_per_sm = (size_t)v;
     *out = h;
     return 0;
 }
@@ -328,6 +428,12 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
     if (nfmax < 4) nfmax = 4;
     if (nfmax > 4 * h->N) nfmax = 4 * h->N;
     h->nfmax = nfmax;
+    return 0;
+}
+
+int cmpc_set_generic(cmpc_handle* h, int on) {
+    if (!h) return fail("null handle");
+    h->force_generic = on ? 1 : 0;
     return 0;
 }
 
@@ -408,6 +514,15 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
     BatchIn bi{Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, mask, h->N, h->W};
     BatchOut bo{u, y, rho, X, nu, status, iters, stats};
     size_t smem; double* hp; size_t stride; int cap;
+    if (!Ad && !h->force_generic) {
+        // raw inputs: v2 fast path (closed-form build, block-packed DMMA factorisation)
+        int grid_f = 0;
+        if (plan_launch_fast(h, h->nfmax, B, &smem, &hp, &stride, &grid_f)) return -1;
+        solve_fast_kernel<<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+        ++g_launches;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
     if (plan_launch(h, h->nfmax, (const void*)solve_kernel, &smem, &hp, &stride, &cap)) return -1;
     const int grid = cap ? (B < cap ? B : cap) : B;
     solve_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
@@ -521,6 +636,47 @@ int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_microbench_dmma(int device, double* dmma_tflops, double* dmma_latency_cycles) {
+    CU_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* out = nullptr;
+    long long* cyc = nullptr;
+    const int tpb = 256, blocks = sms * 8;
+    CU_TRY(cudaMalloc(&out, (size_t)tpb * blocks * sizeof(double)));
+    CU_TRY(cudaMalloc(&cyc, sizeof(long long)));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    if (dmma_tflops) {
+        const int iters = 1 << 12;
+        dmma_peak_kernel<<<blocks, tpb>>>(out, 16);
+        CU_TRY(cudaEventRecord(e0));
+        dmma_peak_kernel<<<blocks, tpb>>>(out, iters);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        g_launches += 2;
+        // one m8n8k4 = 256 FMA = 512 flop per warp
+        *dmma_tflops = 512.0 * 8.0 * iters * (double)(tpb / 32) * blocks / (ms * 1e-3) / 1e12;
+    }
+    if (dmma_latency_cycles) {
+        const int iters = 4096;
+        dmma_latency_kernel<<<1, 32>>>(out, cyc, iters);
+        long long hc = 0;
+        CU_TRY(cudaMemcpy(&hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost));
+        ++g_launches;
+        *dmma_latency_cycles = (double)hc / iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    cudaFree(cyc);
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -70,6 +70,11 @@ int cmpc_set_params(cmpc_handle* h, const double Q[12], const double R[12], doub
  * gait) lets two CTAs share one SM.  Robots exceeding it get status CMPC_TOO_MANY_FEET.          */
 int cmpc_set_max_stance(cmpc_handle* h, int nfmax);
 
+/* Diagnostics: on != 0 routes raw-input calls through the generic kernel (the one used when the
+ * caller supplies Ad/Bd/gd of arbitrary structure) instead of the closed-form fast kernel, so the
+ * two implementations can be compared on the same inputs.                                        */
+int cmpc_set_generic(cmpc_handle* h, int on);
+
 /* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
 int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
                        double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);
@@ -124,6 +129,9 @@ long long cmpc_launch_count(void);
 /* Micro-benchmarks used for the roofline denominators that MEASURED_PEAKS.json lacks
  * (SURVEY.md section 8d): FP64 FMA throughput (TFLOP/s) and shared-memory read bandwidth (GB/s). */
 int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs);
+
+/* FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) and dependent-issue latency (cycles). */
+int cmpc_microbench_dmma(int device, double* dmma_tflops, double* dmma_latency_cycles);
 
 const char* cmpc_last_error(void);
 const char* cmpc_version(void);

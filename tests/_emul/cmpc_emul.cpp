@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_core.cuh"
+#include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_fast.cuh"
 
 using namespace cmpc;
 
@@ -96,6 +97,37 @@ int emul_solve(const Params* p, int B, int N, int nfmax, const double* Ad, const
         solve_one(c, *p, in, o, w, nfmax, warm);
     }
     return 0;
+}
+
+// v2 (raw-input fast path): same outputs, block-packed factor, closed-form build
+int emul_solve_fast(const Params* p, int B, int N, int nfmax, const double* x0, const double* x_ref,
+                    const double* r_foot, const double* I_world, const double* mass, double dt,
+                    const uint64_t* mask, int warm, double* u, double* y, double* rho, double* X, double* nu,
+                    int32_t* status, int32_t* iters, double* stats) {
+    fast::WsF w;
+    std::vector<unsigned char> buf(fast::ws_carve_fast(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr) + 64);
+    fast::ws_carve_fast(w, buf.data(), N, nfmax, nullptr);
+    fast::Cx c = fast::make_cx(0, 1);
+    fast::init_tables(c, w);
+    for (int b = 0; b < B; ++b) {
+        QpIn in = make_in(b, N, nullptr, nullptr, nullptr, x0, x_ref, r_foot, I_world, mass, dt, mask);
+        QpOut o;
+        o.u = u + (size_t)b * 12 * N;
+        o.y = y + (size_t)b * 28 * N;
+        o.rho = rho ? rho + b : nullptr;
+        o.X = X ? X + (size_t)b * 12 * N : nullptr;
+        o.nu = nu ? nu + (size_t)b * 12 * N : nullptr;
+        o.status = status + b;
+        o.iters = iters + b;
+        o.stats = stats + (size_t)b * NSTAT;
+        fast::solve_one_fast(c, *p, in, o, w, nfmax, warm);
+    }
+    return 0;
+}
+
+size_t emul_ws_bytes_fast(int N, int nfmax) {
+    fast::WsF w;
+    return fast::ws_carve_fast(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr);
 }
 
 size_t emul_ws_bytes(int N, int nfmax) {

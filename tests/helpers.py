@@ -13,6 +13,7 @@ EMUL_DIR = os.path.join(ROOT, "tests", "_emul")
 EMUL_SRC = os.path.join(EMUL_DIR, "cmpc_emul.cpp")
 EMUL_LIB = os.path.join(EMUL_DIR, "libcmpc_emul.so")
 CORE = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh")
+FAST = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_fast.cuh")
 
 PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])
 
@@ -47,9 +48,10 @@ def force_error(u, u_star):
 # ------------------------------------------------------------------------------------------------
 def build_emul():
     stale = (not os.path.exists(EMUL_LIB) or
-             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE)))
+             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST)))
     if stale:
-        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", EMUL_LIB, EMUL_SRC], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMUL_LIB, EMUL_SRC],
+                       check=True)
     return ctypes.CDLL(EMUL_LIB)
 
 
@@ -114,4 +116,21 @@ class Emul:
         self.lib.emul_solve(self.params(**kw), B, N, nfmax, _p(Ad), _p(Bd), _p(gd), _p(rec.x0), _p(rec.x_ref),
                             _p(rec.r_foot), _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
                             _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats))
+        return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask)
+
+    def solve_fast(self, rec, mask=None, nfmax=None, warm=0, state=None, **kw):
+        """v2 raw-input path (csrc/cmpc_fast.cuh) under the same one-thread-CTA emulation."""
+        B, N = rec.B, rec.N
+        nfmax = 4 * N if nfmax is None else nfmax
+        if mask is None:
+            mask = self.contact_table(rec.t0, rec.dt, N, rec.gait_hz, rec.duty)
+        if state is None:
+            u = np.zeros((B, 12 * N)); y = np.zeros((B, 28 * N)); rho = np.zeros(B)
+        else:
+            u, y, rho = state
+        X = np.zeros((B, 12 * N)); nu = np.zeros((B, 12 * N))
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); stats = np.zeros((B, 8))
+        self.lib.emul_solve_fast(self.params(**kw), B, N, nfmax, _p(rec.x0), _p(rec.x_ref), _p(rec.r_foot),
+                                 _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
+                                 _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats))
         return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask)

@@ -215,6 +215,37 @@ def test_AdBd_path_equals_device_dynamics_path(mod):
     assert np.abs(a - b).max() < 1e-6
 
 
+def test_fast_kernel_equals_generic_kernel(mod):
+    """Raw inputs through the closed-form fast kernel and through the generic (recursion) kernel."""
+    rec = records.random_records(256, seed=123, stress=0.4)
+    mpc_f, traj = make_mpc(mod, rec)
+    mpc_g, _ = make_mpc(mod, rec, generic_kernel=True)
+    a = mpc_f.solve_QP(None, traj)
+    b = mpc_g.solve_QP(None, traj)
+    assert (a["status"].cpu().numpy() == 1).all() and (b["status"].cpu().numpy() == 1).all()
+    assert float((a["u"] - b["u"]).abs().max()) < 1e-6
+    assert float((a["x"].tensor - b["x"].tensor).abs().max()) < 1e-6
+    assert float((a["lam_a"].tensor - b["lam_a"].tensor).abs().max()) < 1e-6
+    assert float((a["lam_x"].tensor - b["lam_x"].tensor).abs().max()) < 1e-6
+    sa, sb = a["stats"].cpu().numpy(), b["stats"].cpu().numpy()
+    assert np.abs(sa[:, 2] - sb[:, 2]).max() < 1e-8 * max(1.0, np.abs(sa[:, 2]).max())
+    assert np.array_equal(sa[:, 3], sb[:, 3])
+
+
+@pytest.mark.parametrize("N,B", [(32, 64), (48, 32)])
+def test_longer_horizons(mod, N, B):
+    """BASELINE configs[3]: N = 32 / 48 (384 / 576 condensed variables); the factor lives in L2-resident
+    global scratch instead of shared memory."""
+    rec = records.random_records(B, N=N, seed=16384 + N, stress=0.2)
+    mpc, traj = make_mpc(mod, rec, max_stance=4 * (int(0.6 * N) + 1))
+    sol = mpc.solve_QP(None, traj)
+    assert (sol["status"].cpu().numpy() == 1).all()
+    u = sol["u"].cpu().numpy()
+    for b in range(0, B, max(1, B // 4)):
+        o = oracle_solution(rec, b)
+        assert force_error(u[b].reshape(-1, order="F"), o["sol"]["U"])[1] < 1.0
+
+
 def test_admm_mode_and_polish(mod):
     rec = records.random_records(32, seed=31, stress=0.3)
     mpc, traj = make_mpc(mod, rec, mode="admm", eps_abs=1e-5, eps_rel=1e-5, max_iter=4000)

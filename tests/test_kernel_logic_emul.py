@@ -52,10 +52,11 @@ def test_dense_build_matches_oracle(emul):
     assert np.abs(g2 - g).max() <= 1e-11 * np.abs(g).max()
 
 
+@pytest.mark.parametrize("impl", ["generic", "fast"])
 @pytest.mark.parametrize("stress", [0.0, 0.5, 1.0])
-def test_forces_match_exact_optimum(emul, stress):
+def test_forces_match_exact_optimum(emul, stress, impl):
     rec = records.random_records(24, seed=100 + int(10 * stress), stress=stress)
-    r = emul.solve(rec)
+    r = emul.solve(rec) if impl == "generic" else emul.solve_fast(rec)
     assert (r["status"] == 1).all()
     for b in range(rec.B):
         o = oracle_solution(rec, b)
@@ -75,27 +76,31 @@ def test_forces_match_exact_optimum(emul, stress):
         assert np.abs(sq["H"] @ w + sq["g"] + lam_x + sq["A"].T @ lam_a).max() < 1e-8
 
 
-def test_admm_mode_is_osqp_like(emul):
+@pytest.mark.parametrize("impl", ["generic", "fast"])
+def test_admm_mode_is_osqp_like(emul, impl):
     """mode 0 = plain ADMM with OSQP's termination rule: residuals below eps, forces only roughly right
     (that is how OSQP itself behaves on this flat QP)."""
     rec = records.random_records(8, seed=31, stress=0.3)
-    r = emul.solve(rec, mode=0, eps_abs=1e-6, eps_rel=1e-6, max_iter=4000)
+    solve = emul.solve if impl == "generic" else emul.solve_fast
+    r = solve(rec, mode=0, eps_abs=1e-6, eps_rel=1e-6, max_iter=4000)
     assert (r["status"] == 1).all() and (r["iters"] > 0).all()
     for b in range(rec.B):
         o = oracle_solution(rec, b)
         assert np.abs(r["u"][b] - o["sol"]["U"]).max() < 0.2
         assert r["stats"][b, 0] < 1e-3 and r["stats"][b, 1] < 1e-4
     # polish on top of ADMM recovers the exact optimum
-    r2 = emul.solve(rec, mode=0, polish=1, eps_abs=1e-4, eps_rel=1e-4)
+    r2 = solve(rec, mode=0, polish=1, eps_abs=1e-4, eps_rel=1e-4)
     for b in range(rec.B):
         o = oracle_solution(rec, b)
         assert force_error(r2["u"][b], o["sol"]["U"])[1] < 1e-3
 
 
-def test_warm_start_and_edge_masks(emul):
+@pytest.mark.parametrize("impl", ["generic", "fast"])
+def test_warm_start_and_edge_masks(emul, impl):
     rec = records.random_records(6, seed=41, stress=0.5)
-    cold = emul.solve(rec)
-    warm = emul.solve(rec, warm=1, state=(cold["u"].copy(), cold["y"].copy(), cold["rho"].copy()))
+    solve = emul.solve if impl == "generic" else emul.solve_fast
+    cold = solve(rec)
+    warm = solve(rec, warm=1, state=(cold["u"].copy(), cold["y"].copy(), cold["rho"].copy()))
     assert np.abs(warm["u"] - cold["u"]).max() < 1e-7
     assert (warm["stats"][:, 6] <= np.maximum(cold["stats"][:, 6], 1)).all()
     N = rec.N
@@ -103,7 +108,7 @@ def test_warm_start_and_edge_masks(emul):
     # all swing: zero forces, multipliers close stationarity; all stance: 192 free variables
     for bits, nfree in ((0, 0), (2 ** 64 - 1, 192)):
         mask = np.full((rec.B, W), bits, dtype=np.uint64)
-        r = emul.solve(rec, mask=mask)
+        r = solve(rec, mask=mask)
         assert (r["status"] == 1).all() and (r["stats"][:, 3] == nfree).all()
         ct = np.full((4, N), 1 if bits else 0)
         for b in range(2):
@@ -111,5 +116,20 @@ def test_warm_start_and_edge_masks(emul):
             assert force_error(r["u"][b], o["sol"]["U"])[1] < 1e-3
             assert np.abs(r["y"][b] - o["sol"]["y"]).max() < 1e-7
     # a bound on stance foot-steps that is too small is reported, never silently truncated
-    r = emul.solve(rec, nfmax=8)
+    r = solve(rec, nfmax=8)
     assert (r["status"] == -20).all()
+
+
+def test_fast_path_equals_generic_path_all_horizons(emul):
+    """The closed-form fast path (cmpc_fast.cuh) and the recursion-based generic path (cmpc_core.cuh)
+    are independent derivations of the same QP: forces, duals, states, co-states and cost agree."""
+    for N, B in ((16, 16), (32, 4), (48, 2)):
+        rec = records.random_records(B, N=N, seed=300 + N, stress=0.4)
+        a, b = emul.solve(rec), emul.solve_fast(rec)
+        assert (a["status"] == 1).all() and (b["status"] == 1).all()
+        assert np.abs(a["u"] - b["u"]).max() < 1e-6
+        assert np.abs(a["y"] - b["y"]).max() < 1e-8
+        assert np.abs(a["X"] - b["X"]).max() < 1e-9
+        assert np.abs(a["nu"] - b["nu"]).max() < 1e-7
+        assert np.abs(a["stats"][:, 2] - b["stats"][:, 2]).max() < 1e-8 * max(1.0, np.abs(a["stats"][:, 2]).max())
+        assert np.array_equal(a["stats"][:, 3], b["stats"][:, 3])
