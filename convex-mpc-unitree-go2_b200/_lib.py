@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcmpc.so")
+LIB_PATH = os.environ.get("CMPC_LIB") or os.path.join(HERE, "libcmpc.so")   # CMPC_LIB: tools load the timing build
 
 c_int = ctypes.c_int
 c_double = ctypes.c_double
@@ -38,6 +38,7 @@ PROTOTYPES = {
     "cmpc_launch_count": (ctypes.c_longlong, []),
     "cmpc_microbench": (c_int, [c_int, c_dp, c_dp]),
     "cmpc_microbench_dmma": (c_int, [c_int, c_dp, c_dp]),
+    "cmpc_microbench_latency": (c_int, [c_int, c_dp]),
     "cmpc_last_error": (ctypes.c_char_p, []),
     "cmpc_version": (ctypes.c_char_p, []),
 }

@@ -28,6 +28,17 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
+def build_timing():
+    """Tools only: the same source with per-phase clock64 accounting -> libcmpc_timing.so."""
+    out = os.path.join(HERE, "libcmpc_timing.so")
+    cmd = [find_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DCMPC_PHASE_TIMING", "-o", out, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stderr)
+        raise RuntimeError("nvcc failed building libcmpc_timing.so")
+    return out
+
+
 def build(force=False, verbose=False):
     """Build ``libcmpc.so`` if missing or older than its sources.  Returns the path."""
     if not force and not is_stale():
@@ -46,4 +57,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        print(build(force=True, verbose=True))

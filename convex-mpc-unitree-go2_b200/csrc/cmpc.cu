@@ -168,6 +168,7 @@ solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm,
     fast::ws_carve_fast(w, smem, bi.N, nfmax, hb_scratch ? hb_scratch + (size_t)blockIdx.x * hb_stride : nullptr);
     const fast::Cx c = fast::make_cx(threadIdx.x, blockDim.x);
     fast::init_tables(c, w);
+    PHASE_KERNEL_BEGIN();
     const int N = bi.N;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         QpIn in = qp_in(bi, b);
@@ -183,6 +184,7 @@ solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm,
         fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
         __syncthreads();
     }
+    PHASE_KERNEL_END();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -246,6 +248,33 @@ __global__ void dmma_latency_kernel(double* out, long long* cycles, int iters) {
     const long long t1 = clock64();
     out[threadIdx.x] = c0 + c1;
     if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
+// single-warp dependent-issue latencies (cycles): 0 DFMA, 1 rsqrt(double), 2 double shuffle, 3 LDS.64
+__global__ void latency_kernel(double* out, long long* cycles, int iters) {
+    __shared__ double sm[64];
+    double v = 1.0 + threadIdx.x * 1e-9;
+    sm[threadIdx.x] = (double)((threadIdx.x * 7 + 1) & 31);
+    sm[threadIdx.x + 32] = 0.0;
+    __syncwarp();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) v = fma(v, 1.0000001, 1e-9);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) v = rsqrt(v) + 1.5;
+    t1 = clock64();
+    if (threadIdx.x == 0) cycles[1] = t1 - t0;     // includes one DADD
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) v = __shfl_sync(0xffffffffu, v, (threadIdx.x + 1) & 31);
+    t1 = clock64();
+    if (threadIdx.x == 0) cycles[2] = t1 - t0;
+    int idx = threadIdx.x;
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) idx = (int)sm[idx];
+    t1 = clock64();
+    if (threadIdx.x == 0) cycles[3] = t1 - t0;     // LDS.64 + F2I
+    out[threadIdx.x] = v + idx;
 }
 
 }  // namespace
@@ -637,6 +666,34 @@ int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs) {
     cudaEventDestroy(e1);
     cudaFree(out);
     CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+#ifdef CMPC_PHASE_TIMING
+/* tools only (libcmpc_timing.so): cycles and visit counts per phase of solve_one_fast since the last reset */
+int cmpc_debug_phase_cycles(double* out /* 2*16 */, int reset) {
+    unsigned long long h[2 * CMPC_NPHASE];
+    CU_TRY(cudaMemcpyFromSymbol(h, cmpc::fast::g_phase_cycles, sizeof(h)));
+    for (int i = 0; i < 2 * CMPC_NPHASE; ++i) out[i] = (double)h[i];
+    if (reset) { memset(h, 0, sizeof(h)); CU_TRY(cudaMemcpyToSymbol(cmpc::fast::g_phase_cycles, h, sizeof(h))); }
+    return 0;
+}
+#endif
+
+int cmpc_microbench_latency(int device, double* out4) {
+    CU_TRY(cudaSetDevice(device));
+    double* out = nullptr;
+    long long* cyc = nullptr;
+    CU_TRY(cudaMalloc(&out, 32 * sizeof(double)));
+    CU_TRY(cudaMalloc(&cyc, 4 * sizeof(long long)));
+    const int iters = 2048;
+    latency_kernel<<<1, 32>>>(out, cyc, iters);
+    long long h[4];
+    CU_TRY(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+    ++g_launches;
+    for (int i = 0; i < 4; ++i) out4[i] = (double)h[i] / iters;
+    cudaFree(out);
+    cudaFree(cyc);
     return 0;
 }
 

@@ -133,6 +133,9 @@ int cmpc_microbench(int device, double* fp64_tflops, double* smem_gbs);
 /* FP64 tensor-core (DMMA m8n8k4) throughput (TFLOP/s) and dependent-issue latency (cycles). */
 int cmpc_microbench_dmma(int device, double* dmma_tflops, double* dmma_latency_cycles);
 
+/* Single-warp dependent-issue latencies in cycles: out4 = {DFMA, rsqrt(double)+DADD, 64-bit shuffle, LDS.64+F2I}. */
+int cmpc_microbench_latency(int device, double* out4);
+
 const char* cmpc_last_error(void);
 const char* cmpc_version(void);
 

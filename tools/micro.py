@@ -6,4 +6,7 @@ lib = _lib.load()
 a, b, c, d = (ctypes.c_double() for _ in range(4))
 _lib.check(lib.cmpc_microbench(0, ctypes.byref(a), ctypes.byref(b)))
 _lib.check(lib.cmpc_microbench_dmma(0, ctypes.byref(c), ctypes.byref(d)))
+lat = (ctypes.c_double * 4)()
+_lib.check(lib.cmpc_microbench_latency(0, lat))
+print(json.dumps({"latency_cycles": {"dfma": lat[0], "rsqrt_plus_dadd": lat[1], "shfl64": lat[2], "lds64_f2i": lat[3]}}))
 print(json.dumps({"fp64_fma_tflops": a.value, "smem_gbs": b.value, "dmma_tflops": c.value, "dmma_latency_cycles": d.value}))

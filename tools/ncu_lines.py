@@ -43,7 +43,7 @@ def function_ranges(path):
     """(start_line, name) for each function-like definition in a source file."""
     out = []
     for i, ln in enumerate(open(path), 1):
-        f = re.match(r"^(?:CMPC_HDN?|__global__|static|inline|template|__device__)[^;]*?\b([A-Za-z_0-9]+)\s*\(", ln)
+        f = re.match(r"^(?:CMPC_HDN?|CMPC_DEV|__global__|static|inline|__device__)[^;]*?\b([A-Za-z_0-9]+)\s*\(", ln)
         if f and not ln.strip().startswith("//"):
             out.append((i, f.group(1)))
     return out
@@ -71,8 +71,8 @@ def main():
     total = sum(v[0] for v in per_line.values())
     total_ex = sum(v[1] for v in per_line.values())
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    src = {"cmpc_core.cuh": os.path.join(here, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh"),
-           "cmpc.cu": os.path.join(here, "convex-mpc-unitree-go2_b200", "csrc", "cmpc.cu")}
+    csrc = os.path.join(here, "convex-mpc-unitree-go2_b200", "csrc")
+    src = {f: os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".cu"))}
     fr = {k: function_ranges(v) for k, v in src.items()}
     per_fn = defaultdict(lambda: [0, 0, 0])
     for (f, l), v in per_line.items():
