@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -161,11 +162,13 @@ solve_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, doub
 
 // v2 fast path (raw inputs): persistent-style grid-stride loop, one CTA per robot at a time,
 // two CTAs resident per SM when the workspace allows it.
+template <bool kExternal>
 __global__ void __launch_bounds__(kThreads, 2)
 solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hb_scratch, size_t hb_stride) {
     extern __shared__ __align__(16) unsigned char smem[];
     fast::WsF w;
-    fast::ws_carve_fast(w, smem, bi.N, nfmax, hb_scratch ? hb_scratch + (size_t)blockIdx.x * hb_stride : nullptr);
+    if (kExternal) fast::ws_carve_fast<2>(w, smem, bi.N, nfmax, hb_scratch + (size_t)blockIdx.x * hb_stride);
+    else fast::ws_carve_fast<1>(w, smem, bi.N, nfmax, nullptr);
     const fast::Cx c = fast::make_cx(threadIdx.x, blockDim.x);
     fast::init_tables(c, w);
     PHASE_KERNEL_BEGIN();
@@ -384,8 +387,10 @@ int plan_launch_fast(cmpc_handle* h, int nfmax, int B, size_t* smem_out, double*
         per_sm = (int)(h->smem_per_sm / (need + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 2) per_sm = 2;      // register file: 256 threads x 128 registers x 2
+        if (const char* e = getenv("CMPC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // diagnostics
     }
-    CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    if (*hb) CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    else CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     *smem_out = need;
     const int cap = h->sm_count * per_sm;
     *grid = B < cap ? B : cap;
@@ -547,7 +552,8 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         // raw inputs: v2 fast path (closed-form build, block-packed DMMA factorisation)
         int grid_f = 0;
         if (plan_launch_fast(h, h->nfmax, B, &smem, &hp, &stride, &grid_f)) return -1;
-        solve_fast_kernel<<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return 0;
