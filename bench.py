@@ -42,8 +42,8 @@ WORKLOAD = "BASELINE configs[2]: 65536 randomized Go2 states+references per GPU,
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="robots per GPU")
     ap.add_argument("--mode", default="active_set", choices=["active_set", "admm"])

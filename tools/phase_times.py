@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from convex_mpc_b200 import _lib, records
 from convex_mpc_b200.centroidal_mpc import BatchedComTraj, CentroidalMPC
 
-NAMES = ["setup", "vectors", "build_H", "cholesky", "backsolve+viol", "trtri", "active_set", "admm", "polish", "rollout", "residuals", "outputs"]
+NAMES = ["setup", "vectors", "build_H", "cholesky", "backsolve+viol", "trtri", "active_set", "admm", "polish", "rollout", "residuals", "outputs", "admm:factor", "admm:iteration", "admm:check", "sub15"]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
 stress = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 mode = sys.argv[3] if len(sys.argv) > 3 else "active_set"
