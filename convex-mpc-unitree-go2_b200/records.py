@@ -152,3 +152,55 @@ def srb_closed_loop_step(rec, Ad, Bd, gd, u0, mpc_period=0.02, rng=None, noise=0
     if noise and rng is not None:
         x_new = x_new + rng.normal(0, noise, x_new.shape)
     return x_new
+
+
+def next_cycle(rec, u_first, mpc_period=0.02):
+    """Closed-loop replay (BASELINE configs[1]): advance every robot of ``rec`` by one
+    MPC period under its first-step forces ``u_first`` (B,12) with the single-rigid-body model the MPC
+    itself uses (com_trajectory.py:234-270, closed-form ZOH), then rebuild the next cycle's record the way
+    ``ComTraj.generate_traj`` does (com_trajectory.py:84-106): constant commanded velocity / yaw rate, the
+    reference restarted from the new position, contact table at the new time, nominal lever arms.
+    Host NumPy: this stands in for MuJoCo + Pinocchio, it is not part of the hot path."""
+    B, N, dt = rec.B, rec.N, rec.dt
+    x = rec.x0
+    yaw_avg = rec.x_ref[:, 5, :].mean(axis=1)
+    cy, sy = np.cos(yaw_avg), np.sin(yaw_avg)
+    f = u_first.reshape(B, 4, 3)
+    F = f.sum(axis=1)
+    r0 = rec.r_foot[:, :, :, 0]                                   # (B,4,3) lever arms of step 0
+    tau = np.einsum("bij,bj->bi", np.linalg.inv(rec.I_world), np.cross(r0, f).sum(axis=1))
+    om = x[:, 9:12]
+    rz_om = np.stack([cy * om[:, 0] + sy * om[:, 1], -sy * om[:, 0] + cy * om[:, 1], om[:, 2]], axis=1)
+    rz_tau = np.stack([cy * tau[:, 0] + sy * tau[:, 1], -sy * tau[:, 0] + cy * tau[:, 1], tau[:, 2]], axis=1)
+    h = dt * dt / 2
+    g = np.zeros(3); g[2] = -9.81
+    xn = x.copy()
+    xn[:, 0:3] += dt * x[:, 6:9] + h * (F / rec.mass[:, None] + g)
+    xn[:, 3:6] += dt * rz_om + h * rz_tau
+    xn[:, 6:9] += dt * (F / rec.mass[:, None] + g)
+    xn[:, 9:12] += dt * tau
+    x_new = x + (mpc_period / dt) * (xn - x)
+    # next record
+    v_des, wz = rec.x_ref[:, 6:9, 0], rec.x_ref[:, 11, 0]
+    t0 = rec.t0 + mpc_period
+    tv = (np.arange(N) + 1) * dt
+    yaw = x_new[:, 5]
+    x_ref = np.zeros_like(rec.x_ref)
+    pos_des = x_new[:, 0:3].copy()
+    pos_des[:, 2] = 0.27
+    x_ref[:, 0:3, :] = pos_des[:, :, None] + v_des[:, :, None] * tv[None, None, :]
+    x_ref[:, 5, :] = yaw[:, None] + wz[:, None] * tv[None, :]
+    x_ref[:, 6:9, :] = v_des[:, :, None]
+    x_ref[:, 11, :] = wz[:, None]
+    R = _rot_zyx(x_new[:, 3], x_new[:, 4], yaw)
+    I_world = np.einsum("bij,j,bkj->bik", R, GO2_I_BODY, R)
+    table = host_contact_table(t0, dt, N, rec.gait_hz, rec.duty)
+    hips = np.array([[HIP_X, HIP_Y], [HIP_X, -HIP_Y], [-HIP_X, HIP_Y], [-HIP_X, -HIP_Y]])
+    c0, s0 = np.cos(yaw), np.sin(yaw)
+    r_foot = np.zeros_like(rec.r_foot)
+    for leg in range(4):
+        st = table[:, leg, :].astype(np.float64)
+        r_foot[:, leg, 0, :] = (c0 * hips[leg, 0] - s0 * hips[leg, 1])[:, None] * st
+        r_foot[:, leg, 1, :] = (s0 * hips[leg, 0] + c0 * hips[leg, 1])[:, None] * st
+        r_foot[:, leg, 2, :] = (-x_new[:, 2])[:, None] * st
+    return Records(x_new, x_ref, r_foot, I_world, rec.mass, t0, dt, rec.gait_hz, rec.duty, N)

@@ -246,6 +246,35 @@ def test_longer_horizons(mod, N, B):
         assert force_error(u[b].reshape(-1, order="F"), o["sol"]["U"])[1] < 1.0
 
 
+def test_closed_loop_replay_1024_robots(mod):
+    """BASELINE configs[1]: 1024 robots, mixed forward / lateral / yaw commands, replayed in closed loop with
+    the warm start the reference uses (previous solution, unshifted, centroidal_mpc.py:92-95).  Every cycle:
+    all QPs solved and self-certified, sampled robots match the oracle's exact optimum, and the warm-started
+    solve equals a cold solve of the same cycle."""
+    rec = records.random_records(1024, seed=1024)
+    traj = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+    mpc = mod.CentroidalMPC(None, traj, verbose=False, max_stance=40)
+    cold = mod.CentroidalMPC(None, traj, verbose=False, max_stance=40)
+    z0 = rec.x0[:, 2].copy()
+    for cycle in range(12):
+        traj = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+        sol = mpc.solve_QP(None, traj)                      # warm-started from cycle - 1
+        st = sol["stats"].cpu().numpy()
+        assert (sol["status"].cpu().numpy() == 1).all(), cycle
+        assert st[:, 0].max() < 1e-7 and st[:, 1].max() < 1e-7
+        u = sol["x"].full()[:, 12 * rec.N:]
+        cold.reset()
+        uc = cold.solve_QP(None, traj)["x"].full()[:, 12 * rec.N:]
+        assert np.abs(u - uc).max() < 1e-6
+        for b in (3, 511, 1000):
+            o = oracle_solution(rec, b)
+            assert force_error(u[b], o["sol"]["U"])[1] < 1e-3, (cycle, b)
+        rec = records.next_cycle(rec, u[:, :12])
+    # the fleet is still standing and moving: height kept, forward speed near the command on average
+    assert np.abs(rec.x0[:, 2] - z0).max() < 0.05
+    assert np.abs(rec.x0[:, 3:5]).max() < 0.5
+
+
 def test_admm_mode_and_polish(mod):
     rec = records.random_records(32, seed=31, stress=0.3)
     mpc, traj = make_mpc(mod, rec, mode="admm", eps_abs=1e-5, eps_rel=1e-5, max_iter=4000)
