@@ -134,8 +134,9 @@ class CentroidalMPC:
       device      CUDA device (default: current)
       mode        "active_set" (default): exact active-set solve with ADMM fallback;
                   "admm": OSQP-equivalent ADMM only, terminated by eps_abs/eps_rel
-      dynamics    "auto" (default): use ``traj.Ad/Bd/gd`` when present, else compute them on the GPU
-                  from ``traj.m, I_com_world, r_*_foot_world``; "traj" / "device" force one
+      dynamics    "auto" (default): form A_d, B_d, g_d on the GPU from ``traj.m, I_com_world,
+                  r_*_foot_world`` when those are present (fast kernel), else use ``traj.Ad/Bd/gd``
+                  (generic kernel); "traj" / "device" force one
       eps_abs, eps_rel, max_iter, polish, check_termination, adaptive_rho_interval, rho0, sigma, alpha
       max_stance  upper bound on stance foot-steps per robot (see cmpc_set_max_stance)
       generic_kernel  diagnostics: solve raw-input batches with the generic kernel (the one that serves
@@ -267,8 +268,13 @@ class CentroidalMPC:
         t["x0"] = self._dev(traj.initial_x_vec, (B, 12))
         t["x_ref"] = self._dev(traj.compute_x_ref_vec(), (B, 12, N))
         have_ab = all(getattr(traj, k, None) is not None for k in ("Ad", "Bd", "gd"))
-        have_raw = getattr(traj, "m", None) is not None and getattr(traj, "I_com_world", None) is not None
-        use_ab = have_ab if self.dynamics == "auto" else (self.dynamics == "traj")
+        have_raw = (getattr(traj, "m", None) is not None and getattr(traj, "I_com_world", None) is not None and
+                    (getattr(traj, "r_foot", None) is not None or
+                     all(getattr(traj, name, None) is not None for name in _LEG_FIELDS)))
+        # "auto": the raw fields win when present -- the reference's own ComTraj carries both (com_trajectory.py:
+        # 39-40,204-207 next to Ad/Bd/gd), and from the raw fields the GPU forms the same A_d, B_d, g_d in closed
+        # form and takes the fast kernel; Ad/Bd/gd alone (arbitrary structure) go to the generic kernel
+        use_ab = (have_ab and not have_raw) if self.dynamics == "auto" else (self.dynamics == "traj")
         if use_ab:
             if not have_ab:
                 raise _lib.CmpcError("dynamics='traj' needs traj.Ad, traj.Bd and traj.gd")
@@ -291,7 +297,14 @@ class CentroidalMPC:
                 else:
                     rf = np.stack([np.asarray(l, dtype=np.float64).reshape(B, 3, N) for l in legs], axis=1)
             t["r_foot"] = self._dev(rf, (B, 4, 3, N))
-            t["dt"] = float(getattr(traj, "dt", None) or (1.0 / getattr(traj, "gait_hz", 3.0)) / N)
+            dt = getattr(traj, "dt", None)
+            if dt is None and have_ab:
+                # the reference does not store its time step; A_d = I + dt A_c has dt at [0, 6] (com_trajectory.py:234-239,278)
+                Ad0 = traj.Ad
+                dt = float(Ad0.reshape(-1, 12, 12)[0, 0, 6]) if not isinstance(Ad0, torch.Tensor) else float(Ad0.reshape(-1, 12, 12)[0, 0, 6].item())
+            if dt is None:
+                dt = (1.0 / getattr(traj, "gait_hz", 3.0)) / N
+            t["dt"] = float(dt)
         # contact mask: the table the reference carries (com_trajectory.py:106), else computed here
         ct = getattr(traj, "contact_table", None)
         if ct is not None:

@@ -202,6 +202,35 @@ def test_drop_in_single_robot_api(mod):
     assert np.abs(sol2["x"].full().flatten() - w_opt).max() < 1e-7
 
 
+def test_reference_style_traj_takes_fast_path(mod):
+    """A traj shaped like the reference's ComTraj: un-batched NumPy fields, Ad/Bd/gd AND the raw members
+    (m, I_com_world, r_*_foot_world) but no stored time step.  'auto' must pick the fast kernel (dt read from
+    A_d[0,6]) and agree with the Ad/Bd route."""
+    rec = records.random_records(1, seed=19, stress=0.6)
+    ct, Ad, Bd, gd = oracle_inputs(rec, 0)
+
+    class Traj:
+        N = rec.N
+        initial_x_vec = rec.x0[0].reshape(12, 1)
+        contact_table = ct
+        m = float(rec.mass[0])
+        I_com_world = rec.I_world[0]
+        r_fl_foot_world, r_fr_foot_world, r_rl_foot_world, r_rr_foot_world = (rec.r_foot[0, i] for i in range(4))
+        def compute_x_ref_vec(self):
+            return rec.x_ref[0]
+    traj = Traj()
+    traj.Ad, traj.Bd, traj.gd = Ad, Bd, gd
+    fast = mod.CentroidalMPC(None, traj, verbose=False)
+    slow = mod.CentroidalMPC(None, traj, verbose=False, dynamics="traj")
+    a = fast.solve_QP(None, traj, False)
+    b = slow.solve_QP(None, traj, False)
+    wa, wb = a["x"].full().flatten(), b["x"].full().flatten()
+    assert np.abs(wa - wb).max() < 1e-6
+    o = oracle_solution(rec, 0)
+    assert force_error(wa[12 * rec.N:], o["sol"]["U"])[1] < 1e-3
+    assert int(a["status"]) == 1 and int(b["status"]) == 1
+
+
 def test_AdBd_path_equals_device_dynamics_path(mod):
     rec = records.random_records(32, seed=77, stress=0.5)
     mpc, traj = make_mpc(mod, rec)
