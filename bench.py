@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--stress", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--prepass", action="store_true", help="Riccati pre-pass ahead of the condensed kernel (A/B timing)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep 1..262144 -> gpurun_out/sweep.json")
     return ap.parse_args()
 
@@ -214,7 +215,7 @@ def main():
     rec = records.random_records(B, seed=65536 + rank, stress=args.stress)
     max_stance = 4 * (int(np.floor(rec.duty * N)) + 1)        # periodic-gait bound on stance foot-steps
     traj = BatchedComTraj.from_records(rec, device=dev)
-    mpc = CentroidalMPC(None, traj, verbose=False, mode=args.mode, max_stance=max_stance, device=dev)
+    mpc = CentroidalMPC(None, traj, verbose=False, mode=args.mode, max_stance=max_stance, device=dev, prepass=args.prepass)
 
     if args.sweep:
         sweep(args, mpc, records, BatchedComTraj, CentroidalMPC, dev, max_stance)
@@ -255,7 +256,7 @@ def main():
     hb = [pin(rec.x0), pin(rec.x_ref), pin(rec.r_foot), pin(rec.I_world), pin(rec.mass), pin(rec.t0)]
     out = (torch.empty(B, 12 * N, dtype=torch.float64).pin_memory(),
            torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
-    mpc_h = CentroidalMPC(None, traj, verbose=False, mode=args.mode, max_stance=max_stance, max_batch=B, device=dev)
+    mpc_h = CentroidalMPC(None, traj, verbose=False, mode=args.mode, max_stance=max_stance, max_batch=B, device=dev, prepass=args.prepass)
 
     def step_host():
         mpc_h._warm_host = 0
@@ -366,7 +367,7 @@ def sweep(args, mpc, records, BatchedComTraj, CentroidalMPC, dev, max_stance):
     for B in [1, 2, 4, 8, 16, 32, 64, 148, 296, 1024, 4096, 16384, 65536, 262144]:
         rec = records.random_records(B, seed=65536, stress=args.stress)
         tr = BatchedComTraj.from_records(rec, device=dev)
-        m = CentroidalMPC(None, tr, verbose=False, mode=args.mode, max_stance=max_stance, device=dev)
+        m = CentroidalMPC(None, tr, verbose=False, mode=args.mode, max_stance=max_stance, device=dev, prepass=args.prepass)
         for _ in range(3):
             m.reset(); m.solve_QP(None, tr)
         ts = []

@@ -5,6 +5,8 @@
 //   dynamics_kernel        com_trajectory.py:221-286          one thread per (robot, step)
 //   build_kernel           centroidal_mpc.py:235-303 (condensed)   one CTA per robot (diagnostic)
 //   solve_kernel           centroidal_mpc.py:69-120           one CTA per robot, everything in smem
+//   solve_fast_kernel      the same from raw inputs (closed-form build, block-packed DMMA Cholesky)
+//   riccati_kernel         nominal pre-pass of the fast path: one warp per robot (cmpc_riccati.cuh)
 //   fp64_peak_kernel / smem_peak_kernel    roofline denominators measured on the box
 #include <cuda_runtime.h>
 
@@ -19,6 +21,7 @@
 #include "../../include/cmpc.h"
 #include "cmpc_core.cuh"
 #include "cmpc_fast.cuh"
+#include "cmpc_riccati.cuh"
 
 using namespace cmpc;
 
@@ -66,6 +69,19 @@ __device__ __forceinline__ QpIn qp_in(const BatchIn& bi, int b) {
     in.mask = bi.mask ? bi.mask + (size_t)b * bi.W : nullptr;
     in.N = N;
     return in;
+}
+
+__device__ __forceinline__ QpOut qp_out(const BatchOut& bo, int b, int N) {
+    QpOut o;
+    o.u = bo.u + (size_t)b * 12 * N;
+    o.y = bo.y + (size_t)b * 28 * N;
+    o.rho = bo.rho ? bo.rho + b : nullptr;
+    o.X = bo.X ? bo.X + (size_t)b * 12 * N : nullptr;
+    o.nu = bo.nu ? bo.nu + (size_t)b * 12 * N : nullptr;
+    o.status = bo.status + b;
+    o.iters = bo.iters + b;
+    o.stats = bo.stats + (size_t)b * NSTAT;
+    return o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +180,8 @@ solve_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, doub
 // two CTAs resident per SM when the workspace allows it.
 template <bool kExternal>
 __global__ void __launch_bounds__(kThreads, 2)
-solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hb_scratch, size_t hb_stride) {
+solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hb_scratch, size_t hb_stride,
+                  const int* __restrict__ worklist, const int* __restrict__ wl_count) {
     extern __shared__ __align__(16) unsigned char smem[];
     fast::WsF w;
     if (kExternal) fast::ws_carve_fast<2>(w, smem, bi.N, nfmax, hb_scratch + (size_t)blockIdx.x * hb_stride);
@@ -173,21 +190,40 @@ solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm,
     fast::init_tables(c, w);
     PHASE_KERNEL_BEGIN();
     const int N = bi.N;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    // with a work-list (robots the Riccati pre-pass could not finish) the loop runs over its entries
+    const int count = worklist ? *wl_count : B;
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int b = worklist ? worklist[it] : it;
         QpIn in = qp_in(bi, b);
-        QpOut o;
-        o.u = bo.u + (size_t)b * 12 * N;
-        o.y = bo.y + (size_t)b * 28 * N;
-        o.rho = bo.rho ? bo.rho + b : nullptr;
-        o.X = bo.X ? bo.X + (size_t)b * 12 * N : nullptr;
-        o.nu = bo.nu ? bo.nu + (size_t)b * 12 * N : nullptr;
-        o.status = bo.status + b;
-        o.iters = bo.iters + b;
-        o.stats = bo.stats + (size_t)b * NSTAT;
+        QpOut o = qp_out(bo, b, N);
         fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
         __syncthreads();
     }
     PHASE_KERNEL_END();
+}
+
+// Nominal pre-pass of the fast path: one warp per robot (cmpc_riccati.cuh); robots it cannot finish are
+// appended to the work-list of the condensed kernel above.
+constexpr int kRicThreads = 128;
+__global__ void __launch_bounds__(kRicThreads, 3)
+riccati_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* __restrict__ gains,
+               size_t gain_stride, int* __restrict__ worklist, int* __restrict__ wl_count, size_t smem_per_warp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    ric::WsR w;
+    ric::ws_carve_ric(w, smem + (size_t)wid * smem_per_warp, bi.N);
+    Cta c;
+    c.tid = lane; c.nt = 32; c.warp = 1;
+    const int gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
+    double* g = gains + (size_t)gw * gain_stride;
+    const int N = bi.N;
+    for (int b = gw; b < B; b += nw) {
+        QpIn in = qp_in(bi, b);
+        QpOut o = qp_out(bo, b, N);
+        const int done = ric::riccati_one(c, p, in, o, w, nfmax, warm, g);
+        if (!done && lane == 0) worklist[atomicAdd(wl_count, 1)] = b;
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,6 +328,12 @@ struct cmpc_handle {
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     Params p;
+    int prepass = 0;       // Riccati pre-pass ahead of the condensed kernel (active-set mode, raw inputs); opt-in
+    // pre-pass slots (work-list, its counter, gain scratch); calls rotate over them so that solves enqueued on
+    // different streams do not share one
+    struct PreSlot { int* worklist = nullptr; int* count = nullptr; double* gains = nullptr; int cap = 0; size_t gain_doubles = 0; };
+    PreSlot pre[4];
+    unsigned pre_next = 0;
     double* hp_scratch = nullptr;   // packed-matrix scratch when it does not fit shared memory
     size_t hp_stride = 0;
     int hp_ctas = 0;
@@ -432,6 +474,7 @@ int cmpc_destroy(cmpc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->hp_scratch) cudaFree(h->hp_scratch);
+    for (auto& ps : h->pre) { if (ps.worklist) cudaFree(ps.worklist); if (ps.count) cudaFree(ps.count); if (ps.gains) cudaFree(ps.gains); }
     auto& q = h->hp;
     void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -462,6 +505,12 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
     if (nfmax < 4) nfmax = 4;
     if (nfmax > 4 * h->N) nfmax = 4 * h->N;
     h->nfmax = nfmax;
+    return 0;
+}
+
+int cmpc_set_prepass(cmpc_handle* h, int on) {
+    if (!h) return fail("null handle");
+    h->prepass = on ? 1 : 0;
     return 0;
 }
 
@@ -552,8 +601,49 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         // raw inputs: v2 fast path (closed-form build, block-packed DMMA factorisation)
         int grid_f = 0;
         if (plan_launch_fast(h, h->nfmax, B, &smem, &hp, &stride, &grid_f)) return -1;
-        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
-        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+        const int* wl = nullptr;
+        const int* wlc = nullptr;
+        if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET) {
+            // Riccati pre-pass: finishes the robots without an active constraint, lists the others
+            ric::WsR wr;
+            const size_t per_warp = (ric::ws_carve_ric(wr, reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20)), h->N) + 15) & ~(size_t)15;
+            const int wpb = kRicThreads / 32;
+            const size_t smem_r = per_warp * wpb;
+            if (smem_r <= h->smem_optin) {
+                int per_sm = (int)(h->smem_per_sm / (smem_r + 1024));
+                if (per_sm > 3) per_sm = 3;
+                if (per_sm < 1) per_sm = 1;
+                const int want = (B + wpb - 1) / wpb, cap = h->sm_count * per_sm;
+                const int grid_r = want < cap ? want : cap;
+                auto& ps = h->pre[h->pre_next++ & 3u];
+                const size_t gd = ric::gain_doubles(h->nfmax);
+                if (ps.cap < B) {
+                    if (ps.worklist) cudaFree(ps.worklist);
+                    ps.worklist = nullptr;
+                    CU_TRY(cudaMalloc(&ps.worklist, (size_t)B * sizeof(int)));
+                    ps.cap = B;
+                }
+                if (!ps.count) CU_TRY(cudaMalloc(&ps.count, sizeof(int)));
+                const size_t need_g = gd * (size_t)h->sm_count * 3 * wpb;
+                if (ps.gain_doubles < need_g) {
+                    if (ps.gains) cudaFree(ps.gains);
+                    ps.gains = nullptr;
+                    CU_TRY(cudaMalloc(&ps.gains, need_g * sizeof(double)));
+                    ps.gain_doubles = need_g;
+                }
+                CU_TRY(cudaFuncSetAttribute((const void*)riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                CU_TRY(cudaMemsetAsync(ps.count, 0, sizeof(int), (cudaStream_t)stream));
+                riccati_kernel<<<grid_r, kRicThreads, smem_r, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd,
+                                                                                  ps.worklist, ps.count, per_warp);
+                ++g_launches;
+                CU_TRY(cudaGetLastError());
+                wl = ps.worklist; wlc = ps.count;
+                const int cap_f = h->sm_count * 2;
+                grid_f = B < cap_f ? B : cap_f;
+            }
+        }
+        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc);
+        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc);
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return 0;

@@ -75,6 +75,13 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax);
  * two implementations can be compared on the same inputs.                                        */
 int cmpc_set_generic(cmpc_handle* h, int on);
 
+/* Nominal pre-pass (opt-in, default off; active-set mode with raw inputs): a Riccati sweep, one warp per
+ * robot, finishes every robot whose unconstrained minimiser already satisfies the friction-pyramid and
+ * fz_min rows (nominal trot) and hands the others to the condensed active-set
+ * kernel through a device work-list.  Results are the same optimum either way; round-1 measurements
+ *  have the first version of the sweep slower than the path it replaces, hence off. */
+int cmpc_set_prepass(cmpc_handle* h, int on);
+
 /* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
 int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
                        double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);

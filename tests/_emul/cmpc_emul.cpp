@@ -11,6 +11,7 @@
 
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_core.cuh"
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_fast.cuh"
+#include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_riccati.cuh"
 
 using namespace cmpc;
 
@@ -121,6 +122,33 @@ int emul_solve_fast(const Params* p, int B, int N, int nfmax, const double* x0, 
         o.iters = iters + b;
         o.stats = stats + (size_t)b * NSTAT;
         fast::solve_one_fast(c, *p, in, o, w, nfmax, warm);
+    }
+    return 0;
+}
+
+// Riccati pre-pass (csrc/cmpc_riccati.cuh) with a one-thread "warp": done[b] = 1 where the robot was finished
+// by the pre-pass (outputs written), 0 where it would go on to the condensed path (outputs untouched).
+int emul_riccati(const Params* p, int B, int N, int nfmax, const double* x0, const double* x_ref,
+                 const double* r_foot, const double* I_world, const double* mass, double dt,
+                 const uint64_t* mask, int warm, double* u, double* y, double* rho, double* X, double* nu,
+                 int32_t* status, int32_t* iters, double* stats, int32_t* done) {
+    ric::WsR w;
+    std::vector<unsigned char> buf(ric::ws_carve_ric(w, reinterpret_cast<unsigned char*>(4096), N) + 64);
+    ric::ws_carve_ric(w, buf.data(), N);
+    std::vector<double> gains(ric::gain_doubles(nfmax));
+    Cta c{0, 1, 1};
+    for (int b = 0; b < B; ++b) {
+        QpIn in = make_in(b, N, nullptr, nullptr, nullptr, x0, x_ref, r_foot, I_world, mass, dt, mask);
+        QpOut o;
+        o.u = u + (size_t)b * 12 * N;
+        o.y = y + (size_t)b * 28 * N;
+        o.rho = rho ? rho + b : nullptr;
+        o.X = X ? X + (size_t)b * 12 * N : nullptr;
+        o.nu = nu ? nu + (size_t)b * 12 * N : nullptr;
+        o.status = status + b;
+        o.iters = iters + b;
+        o.stats = stats + (size_t)b * NSTAT;
+        done[b] = ric::riccati_one(c, *p, in, o, w, nfmax, warm, gains.data());
     }
     return 0;
 }

@@ -14,6 +14,7 @@ EMUL_SRC = os.path.join(EMUL_DIR, "cmpc_emul.cpp")
 EMUL_LIB = os.path.join(EMUL_DIR, "libcmpc_emul.so")
 CORE = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh")
 FAST = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_fast.cuh")
+RIC = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_riccati.cuh")
 
 PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])
 
@@ -48,7 +49,7 @@ def force_error(u, u_star):
 # ------------------------------------------------------------------------------------------------
 def build_emul():
     stale = (not os.path.exists(EMUL_LIB) or
-             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST)))
+             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST), os.path.getmtime(RIC)))
     if stale:
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMUL_LIB, EMUL_SRC],
                        check=True)
@@ -134,3 +135,21 @@ class Emul:
                                  _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
                                  _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats))
         return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask)
+
+    def riccati(self, rec, mask=None, nfmax=None, warm=0, state=None, **kw):
+        """Riccati pre-pass (csrc/cmpc_riccati.cuh); ``done`` marks the robots it finished."""
+        B, N = rec.B, rec.N
+        nfmax = 4 * N if nfmax is None else nfmax
+        if mask is None:
+            mask = self.contact_table(rec.t0, rec.dt, N, rec.gait_hz, rec.duty)
+        if state is None:
+            u = np.zeros((B, 12 * N)); y = np.zeros((B, 28 * N)); rho = np.zeros(B)
+        else:
+            u, y, rho = state
+        X = np.zeros((B, 12 * N)); nu = np.zeros((B, 12 * N))
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); stats = np.zeros((B, 8))
+        done = np.zeros(B, np.int32)
+        self.lib.emul_riccati(self.params(**kw), B, N, nfmax, _p(rec.x0), _p(rec.x_ref), _p(rec.r_foot),
+                              _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
+                              _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats), _p(done))
+        return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask, done=done)

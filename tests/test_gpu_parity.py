@@ -171,6 +171,31 @@ def test_forces_match_exact_optimum(mod, stress, B):
     assert worst < 1e-6        # in practice the active-set path is exact to ~1e-9 N
 
 
+def test_riccati_prepass_same_optimum(mod):
+    """cmpc_set_prepass(1): warp-per-robot Riccati sweep + device work-list for the rest.  Same statuses, paths
+    and forces as the condensed kernel alone, forces within tolerance of the oracle's exact optimum."""
+    rec = records.random_records(2048, seed=611, stress=0.3)
+    a, traj = make_mpc(mod, rec, prepass=True, max_stance=40)
+    b, _ = make_mpc(mod, rec, max_stance=40)
+    sa, sb = a.solve_QP(None, traj), b.solve_QP(None, traj)
+    ua, ub = sa["u"].cpu().numpy(), sb["u"].cpu().numpy()
+    assert (sa["status"].cpu().numpy() == 1).all() and (sb["status"].cpu().numpy() == 1).all()
+    sta, stb = sa["stats"].cpu().numpy(), sb["stats"].cpu().numpy()
+    assert np.array_equal(sta[:, 7], stb[:, 7])                  # same path per robot
+    assert 0.2 < (sta[:, 7] == 0).mean() < 0.9                   # both kinds present
+    assert np.abs(ua - ub).max() < 1e-7
+    assert np.abs(sa["x"].full() - sb["x"].full()).max() < 1e-7
+    assert np.abs(sa["lam_a"].full() - sb["lam_a"].full()).max() < 1e-6
+    assert sta[:, 1].max() < 1e-6 and sta[:, 0].max() < 1e-9
+    assert sta[sta[:, 7] == 0, 1].max() < 1e-10                  # certificate of the Riccati-finished robots
+    for bi in range(0, 2048, 256):
+        o = oracle_solution(rec, bi)
+        assert force_error(ua[bi].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+    # warm start of the second cycle goes through the same two kernels
+    sa2 = a.solve_QP(None, traj)
+    assert np.abs(sa2["u"].cpu().numpy() - ub).max() < 1e-7
+
+
 def test_drop_in_single_robot_api(mod):
     """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
     rec = records.random_records(1, seed=9, stress=1.0)

@@ -133,3 +133,23 @@ def test_fast_path_equals_generic_path_all_horizons(emul):
         assert np.abs(a["nu"] - b["nu"]).max() < 1e-7
         assert np.abs(a["stats"][:, 2] - b["stats"][:, 2]).max() < 1e-8 * max(1.0, np.abs(a["stats"][:, 2]).max())
         assert np.array_equal(a["stats"][:, 3], b["stats"][:, 3])
+
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_riccati_prepass_finishes_exactly_the_unconstrained_robots(emul, N):
+    """csrc/cmpc_riccati.cuh: the pre-pass must finish the robots whose optimum has no active inequality --
+    with the condensed path's outputs -- and leave every other robot untouched for the condensed kernel."""
+    rec = records.random_records(24, N=N, seed=5, stress=0.2)
+    a = emul.riccati(rec)
+    b = emul.solve_fast(rec)
+    done = a["done"].astype(bool)
+    assert np.array_equal(done, b["stats"][:, 7] == 0)           # same set as PATH_UNCONSTRAINED
+    assert done.any() and (~done).any()
+    for key, tol in (("u", 1e-8), ("y", 1e-8), ("X", 1e-9), ("nu", 1e-8)):
+        assert np.abs(a[key][done] - b[key][done]).max() < tol, key
+    assert (a["status"][done] == 1).all() and a["stats"][done, 1].max() < 1e-10     # r_dual certificate
+    assert np.abs(a["stats"][done, 2] - b["stats"][done, 2]).max() < 1e-9           # objective
+    assert np.abs(a["u"][~done]).max() == 0.0 and (a["status"][~done] == 0).all()   # nothing written
+    for bi in np.flatnonzero(done)[:3]:
+        o = oracle_solution(rec, bi)
+        assert force_error(a["u"][bi], o["sol"]["U"])[1] < 1e-3
