@@ -27,6 +27,8 @@ PROTOTYPES = {
     "cmpc_set_prepass": (c_int, [c_void_p, c_int]),
     "cmpc_contact_table": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, c_double, c_dp,
                                    c_void_p, c_void_p]),
+    "cmpc_generate_traj": (c_int, [c_int, c_int, c_int] + [c_void_p] * 5 + [c_double, c_double, c_double, c_dp, c_dp] +
+                           [c_void_p] * 4 + [c_void_p]),
     "cmpc_pack_contact": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "cmpc_dynamics": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                               c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,0 +1,104 @@
+"""Batched, GPU-resident stand-in for the reference's ``ComTraj`` (``convex_mpc/com_trajectory.py:8-211``):
+the producer of the MPC's inputs.  ``generate_traj`` keeps the reference's argument list;
+the robot model argument becomes a plain state record with a leading batch dimension because Pinocchio is only
+used there to place a joint-less floating base (go2_robot_data.py:224-248).
+
+    gait = Gait(3.0, 0.6)
+    traj = ComTraj(state, hip_offset=HIP, device="cuda:0")
+    traj.generate_traj(state, gait, time_now, vx_body, vy_body, z_des, yaw_rate, time_step)
+    sol = CentroidalMPC(None, traj).solve_QP(None, traj)
+
+All arithmetic runs in ``cmpc_generate_traj`` (csrc/cmpc_traj.cuh); PyTorch only owns the buffers.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .centroidal_mpc import PHASE_OFFSET, BatchedComTraj
+
+
+@dataclass
+class Gait:
+    """gait.py:11-19: frequency, duty and the derived periods."""
+    gait_hz: float
+    gait_duty: float
+
+    @property
+    def gait_period(self):
+        return 1 / self.gait_hz
+
+    @property
+    def stance_time(self):
+        return self.gait_duty * self.gait_period
+
+    @property
+    def swing_time(self):
+        return (1 - self.gait_duty) * self.gait_period
+
+
+@dataclass
+class RobotState:
+    """What ``generate_traj`` reads from ``PinGo2Model`` (com_trajectory.py:37-40,71,116,125; go2_robot_data.py):
+    x (B,12) = compute_com_x_vec(); R_world_to_body (B,3,3); foot_lever_world (B,4,3) legs FL FR RL RR;
+    mass (B,) and inertia (B,3,3) = data.Ig.mass / data.Ig.inertia."""
+    x: torch.Tensor
+    R_world_to_body: torch.Tensor
+    foot_lever_world: torch.Tensor
+    mass: torch.Tensor
+    inertia: torch.Tensor
+
+
+def _dev(a, device, shape):
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float64))
+    t = t.to(device=device, dtype=torch.float64).reshape(shape).contiguous()
+    return t
+
+
+class ComTraj(BatchedComTraj):
+    def __init__(self, state, *, hip_offset, device=None, phase_offset=PHASE_OFFSET):
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise _lib.CmpcError("ComTraj.generate_traj runs on a CUDA device only (no CPU fallback)")
+        self._lib = _lib.load()
+        x = _dev(state.x, self.device, (-1, 12))
+        self.B = x.shape[0]
+        self.pos_des_world = x[:, 0:3].clone()                     # com_trajectory.py:10-13
+        self.hip_offset = np.ascontiguousarray(hip_offset, dtype=np.float64).reshape(4, 3)
+        self.phase_offset = tuple(phase_offset)
+        self.N = None
+
+    def generate_traj(self, state, gait, time_now, x_vel_des_body, y_vel_des_body, z_pos_des_body,
+                      yaw_rate_des_body, time_step, stream=None):
+        """com_trajectory.py:27-211, batched.  Scalars broadcast over the batch; ``time_now`` and the four commands
+        may be per-robot tensors."""
+        B, dev = self.B, self.device
+        N = int(gait.gait_period / time_step)                      # com_trajectory.py:66
+        x0 = _dev(state.x, dev, (B, 12))
+        R_wb = _dev(state.R_world_to_body, dev, (B, 3, 3))
+        lever = _dev(state.foot_lever_world, dev, (B, 4, 3))
+
+        def per_robot(v):
+            t = v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v, dtype=np.float64))
+            return t.to(device=dev, dtype=torch.float64).reshape(-1).expand(B) if t.numel() == 1 else t.to(dev, torch.float64).reshape(B)
+        cmd = torch.stack([per_robot(x_vel_des_body), per_robot(y_vel_des_body), per_robot(z_pos_des_body),
+                           per_robot(yaw_rate_des_body)], dim=1).contiguous()
+        t0 = per_robot(time_now).contiguous()
+        if self.N != N:
+            self._x_ref_buf = torch.empty(B, 12, N, dtype=torch.float64, device=dev)
+            self._r_foot_buf = torch.empty(B, 4, 3, N, dtype=torch.float64, device=dev)
+        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.cmpc_generate_traj(
+                dev.index or 0, N, B, x0.data_ptr(), R_wb.data_ptr(), lever.data_ptr(), cmd.data_ptr(), t0.data_ptr(),
+                float(time_step), float(gait.gait_hz), float(gait.gait_duty), _lib.darr(self.phase_offset),
+                _lib.darr(self.hip_offset.reshape(-1)), self.pos_des_world.data_ptr(), self.pos_des_world.data_ptr(),
+                self._x_ref_buf.data_ptr(), self._r_foot_buf.data_ptr(), ctypes.c_void_p(s)))
+        self._keep = (x0, R_wb, lever, cmd, t0)                    # inputs stay alive until the stream has run
+        BatchedComTraj.__init__(self, N, x0, self._x_ref_buf, time_step, m=_dev(state.mass, dev, (B,)),
+                                I_com_world=_dev(state.inertia, dev, (B, 3, 3)), r_foot=self._r_foot_buf,
+                                time_now=t0, gait_hz=gait.gait_hz, gait_duty=gait.gait_duty,
+                                phase_offset=self.phase_offset)
+        return self

@@ -22,6 +22,7 @@
 #include "cmpc_core.cuh"
 #include "cmpc_fast.cuh"
 #include "cmpc_riccati.cuh"
+#include "cmpc_traj.cuh"
 
 using namespace cmpc;
 
@@ -224,6 +225,30 @@ riccati_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, do
         if (!done && lane == 0) worklist[atomicAdd(wl_count, 1)] = b;
         __syncwarp();
     }
+}
+
+// Batched ComTraj.generate_traj (cmpc_traj.cuh): one thread per (robot, leg).
+__global__ void generate_traj_kernel(int B, int N, const double* __restrict__ x0, const double* __restrict__ R_wb,
+                                     const double* __restrict__ lever, const double* __restrict__ cmd,
+                                     const double* __restrict__ t0, double dt, double period, double duty,
+                                     double o0, double o1, double o2, double o3, double h0, double h1, double h2,
+                                     double h3, double h4, double h5, double h6, double h7, double h8, double h9,
+                                     double h10, double h11, const double* pos_des_in, double* pos_des_out,
+                                     double* __restrict__ x_ref, double* __restrict__ r_foot) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * B) return;
+    const int b = e >> 2, leg = e & 3;
+    const double off = leg == 0 ? o0 : (leg == 1 ? o1 : (leg == 2 ? o2 : o3));
+    const double hipv[12] = {h0, h1, h2, h3, h4, h5, h6, h7, h8, h9, h10, h11};
+    double pin[3];
+    for (int a = 0; a < 3; ++a) pin[a] = pos_des_in[(size_t)b * 3 + a];
+    // every thread of a robot has read pos_des_in before lane (leg 0) may overwrite it in place:
+    // the four threads of a robot sit in one warp
+    __syncwarp();
+    traj::generate_leg(N, leg, x0 + (size_t)b * 12, R_wb + (size_t)b * 9, lever + (size_t)b * 12 + 3 * leg,
+                       cmd + (size_t)b * 4, t0[b], dt, period, duty, off, hipv + 3 * leg, pin,
+                       pos_des_out ? pos_des_out + (size_t)b * 3 : nullptr, x_ref + (size_t)b * 12 * N,
+                       r_foot + ((size_t)b * 4 + leg) * 3 * N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,6 +555,28 @@ int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, doubl
     const int tpb = 128;
     contact_table_kernel<<<(B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
         B, h->N, h->W, t0, dt, period, duty, phase_offset[0], phase_offset[1], phase_offset[2], phase_offset[3], mask_out);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_generate_traj(int device, int N, int B, const double* x0, const double* R_world_to_body, const double* foot_lever,
+                       const double* cmd, const double* t0, double dt, double gait_hz, double duty,
+                       const double phase_offset[4], const double hip_offset[12], const double* pos_des_in,
+                       double* pos_des_out, double* x_ref, double* r_foot, void* stream) {
+    if (!x0 || !R_world_to_body || !foot_lever || !cmd || !t0 || !phase_offset || !hip_offset || !pos_des_in || !x_ref || !r_foot)
+        return fail("null argument");
+    if (N < 1 || N > 48) return fail("horizon N must be in [1, 48]");
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(device));
+    const double period = 1 / gait_hz;   // gait.py:17
+    const int tpb = 128, total = 4 * B;
+    const double* h = hip_offset;
+    generate_traj_kernel<<<(total + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
+        B, N, x0, R_world_to_body, foot_lever, cmd, t0, dt, period, duty, phase_offset[0], phase_offset[1], phase_offset[2],
+        phase_offset[3], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], pos_des_in, pos_des_out,
+        x_ref, r_foot);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -1,0 +1,106 @@
+// cmpc_traj.cuh -- batched ComTraj.generate_traj: the producer of the hot path's inputs.
+//
+// Replaces, per robot and per MPC cycle (reference: ltinphan/convex-mpc-unitree-go2, convex_mpc/):
+//   com_trajectory.py:44-61    clamp of the world position target to +-0.1 m around the CoM, z from the command
+//   com_trajectory.py:64-103   reference trajectory: p_des + v_world t, yaw + yaw_rate t, constant v_world / yaw rate
+//   com_trajectory.py:108-201  lever arms CoM->foot over the horizon: take-off / touch-down state machine on the
+//                              gait mask sampled at time_now + i dt (gait.py:21-24: NO half-step offset, unlike the
+//                              contact table of gait.py:26-37), zero while in swing
+//   gait.py:40-74              touchdown prediction at take-off (hip under the yawed base + drift + yaw correction),
+//                              with the reference's quirk that the drift uses the BODY-frame velocity
+//                              (com_trajectory.py:125-131 -> gait.py:42,58)
+// Pinocchio is only used there to place a joint-less floating base (go2_robot_data.py:224-248), so the kinematics
+// reduce to closed form; the hip offsets (go2_robot_data.py:147-161) are constants passed in by the caller.
+//
+// One thread per (robot, leg): the thread of leg l writes rows 3l..3l+2 of x_ref ([p; rpy; v; omega]) and the
+// three lever-arm rows of its leg -- every row is N contiguous doubles.  HBM-bound and tiny: ~0.4 KB in,
+// 3 KB out per robot.
+#pragma once
+#include "cmpc_core.cuh"
+
+namespace cmpc {
+namespace traj {
+
+// gait mask at time_now + i dt as compute_current_mask forms it (gait.py:21-24 -> 26-37 with dt = 0, N = 1):
+//   t = time_now + i*time_step   (com_trajectory.py:120);  inside: t + arange(1)*0 + 0/2 leaves t unchanged
+CMPC_HD int stance_bit_now(double t0, double dt, int i, double period, double offset, double duty) {
+    const double t = dadd_rn(t0, dmul_rn((double)i, dt));
+    const double ph = dadd_rn(offset, ddiv_rn(t, period));
+    double r = fmod(ph, 1.0);
+    if (r != 0.0 && r < 0.0) r = dadd_rn(r, 1.0);
+    return r < duty ? 1 : 0;
+}
+
+// pos_des after the clamp (com_trajectory.py:44-61)
+CMPC_HD void clamp_pos_des(const double* x0, const double* pos_des_in, double z_des, double out[3]) {
+    const double max_err = 0.1;
+    for (int a = 0; a < 2; ++a) {
+        double v = pos_des_in[a];
+        if (v - x0[a] > max_err) v = x0[a] + max_err;
+        if (x0[a] - v > max_err) v = x0[a] - max_err;
+        out[a] = v;
+    }
+    out[2] = z_des;
+}
+
+// One (robot, leg).  x_ref: the robot's (12, N) block; r_leg: the leg's (3, N) block; pos_des_out may be null.
+CMPC_HD void generate_leg(int N, int leg, const double* x0, const double* R_wb, const double* lever, const double* cmd,
+                          double t0, double dt, double period, double duty, double offset, const double* hip,
+                          const double* pos_des_in, double* pos_des_out, double* x_ref, double* r_leg) {
+    double pd[3];
+    clamp_pos_des(x0, pos_des_in, cmd[2], pd);
+    const double yaw = x0[5], yaw_rate = cmd[3];
+    const double c0 = cos(yaw), s0 = sin(yaw);
+    const double vw[3] = {c0 * cmd[0] - s0 * cmd[1], s0 * cmd[0] + c0 * cmd[1], 0.0};   // R_z [vx, vy, 0]
+    // rows 3 leg .. 3 leg + 2 of the reference (com_trajectory.py:84-103); column i <-> time (i+1) dt
+    for (int i = 0; i < N; ++i) {
+        const double t = ((double)i + 1.0) * dt;
+        double v0, v1, v2;
+        if (leg == 0) { v0 = pd[0] + vw[0] * t; v1 = pd[1] + vw[1] * t; v2 = pd[2] + vw[2] * t; }
+        else if (leg == 1) { v0 = 0.0; v1 = 0.0; v2 = yaw + yaw_rate * t; }
+        else if (leg == 2) { v0 = vw[0]; v1 = vw[1]; v2 = vw[2]; }
+        else { v0 = 0.0; v1 = 0.0; v2 = yaw_rate; }
+        x_ref[(3 * leg) * N + i] = v0;
+        x_ref[(3 * leg + 1) * N + i] = v1;
+        x_ref[(3 * leg + 2) * N + i] = v2;
+    }
+    if (leg == 0 && pos_des_out) { pos_des_out[0] = pd[0]; pos_des_out[1] = pd[1]; pos_des_out[2] = pd[2]; }
+    // lever arms (com_trajectory.py:108-201)
+    const double t_swing = (1.0 - duty) * period, t_stance = duty * period;   // gait.py:18-19
+    const double pred = (t_swing + 0.5 * t_stance) / 2.0;                     // gait.py:53-54
+    // body-frame velocity of the dummy model: R_world_to_body of the REAL robot times the reference velocity
+    const double vb0 = R_wb[0] * vw[0] + R_wb[1] * vw[1] + R_wb[2] * vw[2];
+    const double vb1 = R_wb[3] * vw[0] + R_wb[4] * vw[1] + R_wb[5] * vw[2];
+    double nx = lever[0], ny = lever[1], nz = lever[2];      // next touchdown lever: starts as the measured one (:116)
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    int prev = 2;
+    for (int i = 0; i < N; ++i) {
+        const int m = stance_bit_now(t0, dt, i, period, offset, duty);
+        if (m != prev) {
+            if (m == 0) {
+                const double t = ((double)i + 1.0) * dt;
+                const double bx = pd[0] + vw[0] * t, by = pd[1] + vw[1] * t, bz = pd[2] + vw[2] * t;
+                const double yi = yaw + yaw_rate * t;
+                const double ci = cos(yi), si = sin(yi);
+                const double hx = ci * hip[0] - si * hip[1], hy = si * hip[0] + ci * hip[1];
+                const double px = bx + hx, py = by + hy;                    // nominal touchdown (hip under the base)
+                const double dth = yaw_rate * pred;
+                const double rx = px - bx, ry = py - by;
+                const double tx = (px + vb0 * pred) + (-dth * ry);
+                const double ty = (py + vb1 * pred) + (dth * rx);
+                const double tz = 0.02;
+                nx = tx - bx; ny = ty - by; nz = tz - bz;
+                cx = 0.0; cy = 0.0; cz = 0.0;
+            } else {
+                cx = nx; cy = ny; cz = nz;
+            }
+        }
+        r_leg[i] = cx;
+        r_leg[N + i] = cy;
+        r_leg[2 * N + i] = cz;
+        prev = m;
+    }
+}
+
+}  // namespace traj
+}  // namespace cmpc

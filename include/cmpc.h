@@ -82,6 +82,20 @@ int cmpc_set_generic(cmpc_handle* h, int on);
  *  have the first version of the sweep slower than the path it replaces, hence off. */
 int cmpc_set_prepass(cmpc_handle* h, int on);
 
+/* ComTraj.generate_traj (com_trajectory.py:27-211 with gait.py:21-24,40-74), batched: reference trajectory,
+ * clamp of the world position target and lever arms CoM->foot over the horizon -- the producer of x_ref and
+ * r_foot for cmpc_solve.  All arrays device, FP64, row-major:
+ *   x0 (B,12) [p, rpy, v, omega];  R_world_to_body (B,3,3) of the real robot (go2_robot_data.py:216);
+ *   foot_lever (B,4,3) measured levers, legs FL FR RL RR (go2_robot_data.py:261-269);
+ *   cmd (B,4) = x_vel_des_body, y_vel_des_body, z_pos_des_body, yaw_rate_des_body;  t0 (B) = time_now;
+ *   hip_offset (4,3) host, body frame (go2_robot_data.py:147-161);  pos_des_in/out (B,3): the target ComTraj
+ *   carries from cycle to cycle (com_trajectory.py:13,47-61), may be the same buffer;
+ *   x_ref (B,12,N), r_foot (B,4,3,N) out.  The contact table for the QP is cmpc_contact_table (gait.py:26-37). */
+int cmpc_generate_traj(int device, int N, int B, const double* x0, const double* R_world_to_body,
+                       const double* foot_lever, const double* cmd, const double* t0, double dt, double gait_hz,
+                       double duty, const double phase_offset[4], const double hip_offset[12],
+                       const double* pos_des_in, double* pos_des_out, double* x_ref, double* r_foot, void* stream);
+
 /* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
 int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
                        double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);

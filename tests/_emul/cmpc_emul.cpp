@@ -12,6 +12,7 @@
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_core.cuh"
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_fast.cuh"
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_riccati.cuh"
+#include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_traj.cuh"
 
 using namespace cmpc;
 
@@ -149,6 +150,21 @@ int emul_riccati(const Params* p, int B, int N, int nfmax, const double* x0, con
         o.iters = iters + b;
         o.stats = stats + (size_t)b * NSTAT;
         done[b] = ric::riccati_one(c, *p, in, o, w, nfmax, warm, gains.data());
+    }
+    return 0;
+}
+
+// ComTraj.generate_traj (csrc/cmpc_traj.cuh), one (robot, leg) at a time
+int emul_generate_traj(int N, int B, const double* x0, const double* R_wb, const double* lever, const double* cmd,
+                       const double* t0, double dt, double gait_hz, double duty, const double* off, const double* hip,
+                       const double* pos_des_in, double* pos_des_out, double* x_ref, double* r_foot) {
+    const double period = 1 / gait_hz;
+    for (int b = 0; b < B; ++b) {
+        double pin[3] = {pos_des_in[3 * b], pos_des_in[3 * b + 1], pos_des_in[3 * b + 2]};
+        for (int leg = 0; leg < 4; ++leg)
+            traj::generate_leg(N, leg, x0 + (size_t)b * 12, R_wb + (size_t)b * 9, lever + (size_t)b * 12 + 3 * leg,
+                               cmd + (size_t)b * 4, t0[b], dt, period, duty, off[leg], hip + 3 * leg, pin,
+                               pos_des_out + (size_t)b * 3, x_ref + (size_t)b * 12 * N, r_foot + ((size_t)b * 4 + leg) * 3 * N);
     }
     return 0;
 }

@@ -15,6 +15,7 @@ EMUL_LIB = os.path.join(EMUL_DIR, "libcmpc_emul.so")
 CORE = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh")
 FAST = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_fast.cuh")
 RIC = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_riccati.cuh")
+TRAJ = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_traj.cuh")
 
 PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])
 
@@ -49,7 +50,7 @@ def force_error(u, u_star):
 # ------------------------------------------------------------------------------------------------
 def build_emul():
     stale = (not os.path.exists(EMUL_LIB) or
-             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST), os.path.getmtime(RIC)))
+             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST), os.path.getmtime(RIC), os.path.getmtime(TRAJ)))
     if stale:
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMUL_LIB, EMUL_SRC],
                        check=True)
@@ -153,3 +154,32 @@ class Emul:
                               _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
                               _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats), _p(done))
         return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask, done=done)
+
+    def generate_traj(self, N, x0, R_wb, lever, cmd, t0, dt, hz, duty, hip, pos_des, off=PHASE_OFFSET):
+        """csrc/cmpc_traj.cuh under the host emulation: returns (pos_des_out, x_ref (B,12,N), r_foot (B,4,3,N))."""
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        x0, R_wb, lever, cmd, t0, hip, pos_des, off = map(c, (x0, R_wb, lever, cmd, t0, hip, pos_des, off))
+        B = x0.shape[0]
+        out_pd = np.zeros((B, 3)); x_ref = np.zeros((B, 12, N)); r_foot = np.zeros((B, 4, 3, N))
+        self.lib.emul_generate_traj(N, B, _p(x0), _p(R_wb), _p(lever), _p(cmd), _p(t0), ctypes.c_double(dt),
+                                    ctypes.c_double(hz), ctypes.c_double(duty), _p(off), _p(hip), _p(pos_des),
+                                    _p(out_pd), _p(x_ref), _p(r_foot))
+        return out_pd, x_ref, r_foot
+
+
+def golden_traj_batches(path=None):
+    """The reference-generated trajectory cases (tests/golden/make_golden_traj.py) grouped by (hz, duty, N)."""
+    path = path or os.path.join(ROOT, "tests", "golden", "reference_traj_vectors.npz")
+    g = np.load(path)
+    groups = {}
+    for i in range(int(g["count"])):
+        k = f"tr{i}_"
+        cfg = tuple(g[k + "cfg"])
+        groups.setdefault(cfg, []).append({f: g[k + f] for f in ("x0", "R_wb", "levers", "mass", "inertia", "pos_des_in", "cmd",
+                                                                "t_now", "pos_des_out", "x_ref", "contact", "r_foot", "Ad", "Bd", "gd")})
+    out = []
+    for (hz, duty, N, dt), cases in groups.items():
+        st = lambda f: np.stack([c[f] for c in cases])
+        out.append(dict(hz=float(hz), duty=float(duty), N=int(N), dt=float(dt), hip=g["hip"],
+                        **{f: st(f) for f in cases[0]}))
+    return out

@@ -153,3 +153,15 @@ def test_riccati_prepass_finishes_exactly_the_unconstrained_robots(emul, N):
     for bi in np.flatnonzero(done)[:3]:
         o = oracle_solution(rec, bi)
         assert force_error(a["u"][bi], o["sol"]["U"])[1] < 1e-3
+
+
+def test_traj_generator_matches_reference_golden(emul):
+    """csrc/cmpc_traj.cuh (host emulation) against the reference's own generate_traj outputs."""
+    from helpers import golden_traj_batches
+    for g in golden_traj_batches():
+        pd, xr, rf = emul.generate_traj(g["N"], g["x0"], g["R_wb"], g["levers"], g["cmd"], g["t_now"], g["dt"], g["hz"],
+                                        g["duty"], g["hip"], g["pos_des_in"])
+        assert np.array_equal(pd, g["pos_des_out"])                            # clamp: exact
+        assert np.array_equal(rf == 0.0, g["r_foot"] == 0.0)                   # take-off / touch-down pattern: exact
+        assert np.abs(xr - g["x_ref"]).max() <= 1e-13 * max(1.0, np.abs(g["x_ref"]).max())
+        assert np.abs(rf - g["r_foot"]).max() <= 1e-14

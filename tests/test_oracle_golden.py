@@ -46,3 +46,20 @@ def test_dynamics_match_reference(golden):
             assert np.abs(Bd - golden[f"dyn{ci}_Bd"]).max() <= 1e-15
             assert np.abs(gd - golden[f"dyn{ci}_gd"]).max() <= 1e-16
             assert gd.shape == (12, 1)
+
+
+def test_traj_generator_restatement_matches_reference():
+    """oracle/traj_ref.py against the reference's own generate_traj (tests/golden/make_golden_traj.py)."""
+    from helpers import golden_traj_batches
+    from oracle import traj_ref
+    n = 0
+    for g in golden_traj_batches():
+        for b in range(g["x0"].shape[0]):
+            pd, xr, rf = traj_ref.generate_traj(g["x0"][b], g["R_wb"][b], g["levers"][b], g["cmd"][b], float(g["t_now"][b]),
+                                                g["dt"], g["N"], g["hz"], g["duty"], g["hip"], g["pos_des_in"][b])
+            assert np.array_equal(pd, g["pos_des_out"][b])
+            assert np.array_equal(xr, g["x_ref"][b])
+            assert np.array_equal(rf == 0.0, g["r_foot"][b] == 0.0)            # swing / stance pattern: exact
+            assert np.abs(rf - g["r_foot"][b]).max() <= 1e-15
+            n += 1
+    assert n == 72
