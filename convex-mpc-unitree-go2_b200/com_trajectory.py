@@ -102,3 +102,29 @@ class ComTraj(BatchedComTraj):
                                 time_now=t0, gait_hz=gait.gait_hz, gait_duty=gait.gait_duty,
                                 phase_offset=self.phase_offset)
         return self
+
+
+def srb_step(state, traj, u, mpc_period, I_body, stance_offset, out=None, stream=None):
+    """Advance every robot by one MPC period with the first-step forces of ``u`` (the solver's (B, 12N) force
+    buffer, entries 0..11 = step 0) under the MPC's own single-rigid-body model -- ``cmpc_srb_step``, the
+    device-resident stand-in for MuJoCo + Pinocchio.  Returns the next ``RobotState``
+    (``out`` is reused when given)."""
+    lib = _lib.load()
+    dev = traj.device
+    B, N = traj.B, traj.N
+    x = _dev(state.x, dev, (B, 12))
+    if out is None:
+        out = RobotState(torch.empty_like(x), torch.empty(B, 3, 3, dtype=torch.float64, device=dev),
+                         torch.empty(B, 4, 3, dtype=torch.float64, device=dev), traj.m,
+                         torch.empty(B, 3, 3, dtype=torch.float64, device=dev))
+    s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    u = u.reshape(B, 12 * N)
+    assert u.is_contiguous() and u.dtype == torch.float64
+    with torch.cuda.device(dev):
+        _lib.check(lib.cmpc_srb_step(dev.index or 0, N, B, x.data_ptr(), u.data_ptr(), traj.compute_x_ref_vec().data_ptr(),
+                                     traj.r_foot.data_ptr(), traj.I_com_world.data_ptr(), traj.m.data_ptr(), float(mpc_period),
+                                     _lib.darr(np.asarray(I_body, dtype=np.float64).reshape(3)),
+                                     _lib.darr(np.asarray(stance_offset, dtype=np.float64).reshape(12)),
+                                     out.x.data_ptr(), out.R_world_to_body.data_ptr(), out.inertia.data_ptr(),
+                                     out.foot_lever_world.data_ptr(), ctypes.c_void_p(s)))
+    return out

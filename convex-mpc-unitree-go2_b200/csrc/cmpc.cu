@@ -251,6 +251,25 @@ __global__ void generate_traj_kernel(int B, int N, const double* __restrict__ x0
                        r_foot + ((size_t)b * 4 + leg) * 3 * N);
 }
 
+// SRB closed-loop step (cmpc_traj.cuh): one thread per robot.
+__global__ void srb_step_kernel(int B, int N, const double* __restrict__ x, const double* __restrict__ u,
+                                const double* __restrict__ x_ref, const double* __restrict__ r_foot,
+                                const double* __restrict__ I_world, const double* __restrict__ mass, double T,
+                                double ib0, double ib1, double ib2, double s0, double s1, double s2, double s3,
+                                double s4, double s5, double s6, double s7, double s8, double s9, double s10,
+                                double s11, double* x_out, double* R_wb_out, double* I_out, double* lever_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double ib[3] = {ib0, ib1, ib2};
+    const double so[12] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11};
+    double xin[12], Iw[9];
+    for (int i = 0; i < 12; ++i) xin[i] = x[(size_t)b * 12 + i];       // x_out / I_out may alias the inputs
+    for (int i = 0; i < 9; ++i) Iw[i] = I_world[(size_t)b * 9 + i];
+    traj::srb_step_one(N, xin, u + (size_t)b * 12 * N, x_ref + (size_t)b * 12 * N, r_foot + (size_t)b * 12 * N, Iw,
+                       mass[b], T, ib, so, x_out + (size_t)b * 12, R_wb_out + (size_t)b * 9, I_out + (size_t)b * 9,
+                       lever_out + (size_t)b * 12);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Roofline denominators: dependent-free DFMA streams and shared-memory 8-byte reads.
 // ---------------------------------------------------------------------------------------------
@@ -577,6 +596,26 @@ int cmpc_generate_traj(int device, int N, int B, const double* x0, const double*
         B, N, x0, R_world_to_body, foot_lever, cmd, t0, dt, period, duty, phase_offset[0], phase_offset[1], phase_offset[2],
         phase_offset[3], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], pos_des_in, pos_des_out,
         x_ref, r_foot);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_srb_step(int device, int N, int B, const double* x, const double* u, const double* x_ref, const double* r_foot,
+                  const double* I_world, const double* mass, double T, const double I_body[3], const double stance_offset[12],
+                  double* x_out, double* R_world_to_body_out, double* I_world_out, double* foot_lever_out, void* stream) {
+    if (!x || !u || !x_ref || !r_foot || !I_world || !mass || !I_body || !stance_offset || !x_out || !R_world_to_body_out ||
+        !I_world_out || !foot_lever_out)
+        return fail("null argument");
+    if (N < 1 || N > 48) return fail("horizon N must be in [1, 48]");
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(device));
+    const int tpb = 128;
+    const double* s = stance_offset;
+    srb_step_kernel<<<(B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
+        B, N, x, u, x_ref, r_foot, I_world, mass, T, I_body[0], I_body[1], I_body[2], s[0], s[1], s[2], s[3], s[4], s[5], s[6],
+        s[7], s[8], s[9], s[10], s[11], x_out, R_world_to_body_out, I_world_out, foot_lever_out);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -102,5 +102,59 @@ CMPC_HD void generate_leg(int N, int leg, const double* x0, const double* R_wb, 
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Single-rigid-body closed-loop step: stands in for MuJoCo + Pinocchio between two MPC
+// cycles so that generate_traj -> solve -> step stays on the device.  The model is the one the MPC itself uses
+// (com_trajectory.py:234-270) held for T seconds under the first-step forces; because A_c^2 = 0 the zero-order
+// hold is exact in closed form:  x(T) = x + T A_c x + (T I + T^2/2 A_c)(B_c u + g_c).
+// Outputs besides the state: R_world_to_body (ZYX Euler, go2_robot_data.py:213-216), the world inertia
+// R I_body R^T, and nominal measured levers (stance offsets under the yawed body, z = -height) -- the three
+// things generate_traj / the MPC read from the robot model.
+// ----------------------------------------------------------------------------------------------
+CMPC_HD void srb_step_one(int N, const double* x, const double* u0, const double* x_ref, const double* r_foot,
+                          const double* I_world, double mass, double T, const double* I_body, const double* stance_off,
+                          double* x_out, double* R_wb_out, double* I_out, double* lever_out) {
+    DynCommon d;
+    dyn_common(d, x_ref, N, I_world, mass, T);
+    double F[3] = {0.0, 0.0, 0.0}, tq[3] = {0.0, 0.0, 0.0};
+    for (int leg = 0; leg < 4; ++leg) {
+        const double* f = u0 + 3 * leg;
+        const double r[3] = {r_foot[(leg * 3 + 0) * N], r_foot[(leg * 3 + 1) * N], r_foot[(leg * 3 + 2) * N]};
+        for (int a = 0; a < 3; ++a) F[a] += f[a];
+        tq[0] += r[1] * f[2] - r[2] * f[1];
+        tq[1] += r[2] * f[0] - r[0] * f[2];
+        tq[2] += r[0] * f[1] - r[1] * f[0];
+    }
+    double al[3];                                           // angular acceleration I^-1 sum r x f
+    for (int i = 0; i < 3; ++i) al[i] = d.Iinv[i * 3] * tq[0] + d.Iinv[i * 3 + 1] * tq[1] + d.Iinv[i * 3 + 2] * tq[2];
+    const double acc[3] = {F[0] * d.minv, F[1] * d.minv, F[2] * d.minv - 9.81};
+    const double h = T * T / 2.0;
+    const double om[3] = {x[9], x[10], x[11]};
+    const double rz_om[3] = {d.cy * om[0] + d.sy * om[1], -d.sy * om[0] + d.cy * om[1], om[2]};
+    const double rz_al[3] = {d.cy * al[0] + d.sy * al[1], -d.sy * al[0] + d.cy * al[1], al[2]};
+    double xn[12];
+    for (int a = 0; a < 3; ++a) {
+        xn[a] = x[a] + T * x[6 + a] + h * acc[a];
+        xn[3 + a] = x[3 + a] + T * rz_om[a] + h * rz_al[a];
+        xn[6 + a] = x[6 + a] + T * acc[a];
+        xn[9 + a] = x[9 + a] + T * al[a];
+    }
+    for (int i = 0; i < 12; ++i) x_out[i] = xn[i];
+    const double cr = cos(xn[3]), sr = sin(xn[3]), cp = cos(xn[4]), sp = sin(xn[4]), cy = cos(xn[5]), sy = sin(xn[5]);
+    const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                         sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                         -sp, cp * sr, cp * cr};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            R_wb_out[i * 3 + j] = R[j * 3 + i];
+            I_out[i * 3 + j] = R[i * 3] * I_body[0] * R[j * 3] + R[i * 3 + 1] * I_body[1] * R[j * 3 + 1] + R[i * 3 + 2] * I_body[2] * R[j * 3 + 2];
+        }
+    for (int leg = 0; leg < 4; ++leg) {
+        lever_out[3 * leg] = cy * stance_off[3 * leg] - sy * stance_off[3 * leg + 1];
+        lever_out[3 * leg + 1] = sy * stance_off[3 * leg] + cy * stance_off[3 * leg + 1];
+        lever_out[3 * leg + 2] = -xn[2];
+    }
+}
+
 }  // namespace traj
 }  // namespace cmpc

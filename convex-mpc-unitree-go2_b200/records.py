@@ -204,3 +204,38 @@ def next_cycle(rec, u_first, mpc_period=0.02):
         r_foot[:, leg, 1, :] = (s0 * hips[leg, 0] + c0 * hips[leg, 1])[:, None] * st
         r_foot[:, leg, 2, :] = (-x_new[:, 2])[:, None] * st
     return Records(x_new, x_ref, r_foot, I_world, rec.mass, t0, dt, rec.gait_hz, rec.duty, N)
+
+
+def srb_step_host(x, u_first, x_ref, r_foot, I_world, mass, T, I_body=GO2_I_BODY, stance_offset=None):
+    """NumPy twin of ``cmpc_srb_step`` (csrc/cmpc_traj.cuh): the MPC's own single-rigid-body model
+    (com_trajectory.py:234-270) held for ``T`` seconds under the first-step forces (exact ZOH, A_c^2 = 0).
+    Returns (x_new (B,12), R_world_to_body (B,3,3), I_world (B,3,3), foot_lever (B,4,3)).  Host stand-in for
+    MuJoCo + Pinocchio; test / workload-generation use only."""
+    if stance_offset is None:
+        stance_offset = np.array([[HIP_X, HIP_Y, 0], [HIP_X, -HIP_Y, 0], [-HIP_X, HIP_Y, 0], [-HIP_X, -HIP_Y, 0]])
+    B = x.shape[0]
+    yaw_avg = x_ref[:, 5, :].mean(axis=1)
+    cy, sy = np.cos(yaw_avg), np.sin(yaw_avg)
+    f = u_first.reshape(B, 4, 3)
+    F = f.sum(axis=1)
+    r0 = r_foot[:, :, :, 0]
+    al = np.einsum("bij,bj->bi", np.linalg.inv(I_world), np.cross(r0, f).sum(axis=1))
+    acc = F / mass[:, None] + np.array([0, 0, -9.81])
+    om = x[:, 9:12]
+    rz = lambda v: np.stack([cy * v[:, 0] + sy * v[:, 1], -sy * v[:, 0] + cy * v[:, 1], v[:, 2]], axis=1)
+    h = T * T / 2
+    xn = x.copy()
+    xn[:, 0:3] += T * x[:, 6:9] + h * acc
+    xn[:, 3:6] += T * rz(om) + h * rz(al)
+    xn[:, 6:9] += T * acc
+    xn[:, 9:12] += T * al
+    R = _rot_zyx(xn[:, 3], xn[:, 4], xn[:, 5])
+    I_new = np.einsum("bij,j,bkj->bik", R, np.asarray(I_body), R)
+    c0, s0 = np.cos(xn[:, 5]), np.sin(xn[:, 5])
+    so = np.asarray(stance_offset)
+    lever = np.zeros((B, 4, 3))
+    for leg in range(4):
+        lever[:, leg, 0] = c0 * so[leg, 0] - s0 * so[leg, 1]
+        lever[:, leg, 1] = s0 * so[leg, 0] + c0 * so[leg, 1]
+        lever[:, leg, 2] = -xn[:, 2]
+    return xn, np.swapaxes(R, 1, 2).copy(), I_new, lever

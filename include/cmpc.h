@@ -96,6 +96,19 @@ int cmpc_generate_traj(int device, int N, int B, const double* x0, const double*
                        double duty, const double phase_offset[4], const double hip_offset[12],
                        const double* pos_des_in, double* pos_des_out, double* x_ref, double* r_foot, void* stream);
 
+/* Single-rigid-body closed-loop step (stand-in for MuJoCo + Pinocchio between two MPC
+ * cycles, model of com_trajectory.py:234-270 held for T seconds under the first-step forces, exact ZOH).
+ *   x (B,12), u (B,12N) as cmpc_solve wrote it (entries 0..11 = step 0), x_ref (B,12,N), r_foot (B,4,3,N),
+ *   I_world (B,3,3), mass (B): the inputs of the cycle just solved;  I_body (3) principal inertias and
+ *   stance_offset (4,3) nominal foot positions in the body frame: host.
+ * Outputs (device): x_out (B,12), R_world_to_body_out (B,3,3), I_world_out (B,3,3), foot_lever_out (B,4,3) --
+ * what cmpc_generate_traj / cmpc_solve read from the robot model for the next cycle.  x_out may alias x and
+ * I_world_out may alias I_world.                                                                        */
+int cmpc_srb_step(int device, int N, int B, const double* x, const double* u, const double* x_ref,
+                  const double* r_foot, const double* I_world, const double* mass, double T, const double I_body[3],
+                  const double stance_offset[12], double* x_out, double* R_world_to_body_out, double* I_world_out,
+                  double* foot_lever_out, void* stream);
+
 /* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
 int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
                        double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);

@@ -169,6 +169,16 @@ int emul_generate_traj(int N, int B, const double* x0, const double* R_wb, const
     return 0;
 }
 
+int emul_srb_step(int N, int B, const double* x, const double* u, const double* x_ref, const double* r_foot,
+                  const double* I_world, const double* mass, double T, const double* I_body, const double* so,
+                  double* x_out, double* R_wb, double* I_out, double* lever) {
+    for (int b = 0; b < B; ++b)
+        traj::srb_step_one(N, x + (size_t)b * 12, u + (size_t)b * 12 * N, x_ref + (size_t)b * 12 * N, r_foot + (size_t)b * 12 * N,
+                           I_world + (size_t)b * 9, mass[b], T, I_body, so, x_out + (size_t)b * 12, R_wb + (size_t)b * 9,
+                           I_out + (size_t)b * 9, lever + (size_t)b * 12);
+    return 0;
+}
+
 size_t emul_ws_bytes_fast(int N, int nfmax) {
     fast::WsF w;
     return fast::ws_carve_fast(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr);

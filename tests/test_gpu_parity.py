@@ -232,6 +232,58 @@ def test_traj_generator_matches_reference_golden_and_feeds_the_mpc(mod):
         assert np.abs(sol["u"].cpu().numpy()[ok] - sol2["u"].cpu().numpy()[ok]).max() < 1e-5
 
 
+def test_device_resident_closed_loop(mod):
+    """generate_traj -> solve_QP -> srb_step on the device for 12 cycles: the SRB step against
+    its NumPy twin, the generated trajectory against the oracle restatement of the reference's generate_traj, and
+    the forces of the last cycle against the oracle's exact optimum."""
+    from convex_mpc_b200 import com_trajectory as ct
+    from oracle import traj_ref
+    B, N, HZ, DUTY, T = 96, 16, 3.0, 0.6, 0.02
+    rng = np.random.default_rng(77)
+    gait = ct.Gait(HZ, DUTY)
+    dt = gait.gait_period / N
+    hip = np.array([[0.1934, 0.0465, 0], [0.1934, -0.0465, 0], [-0.1934, 0.0465, 0], [-0.1934, -0.0465, 0]])
+    so = np.array([[0.1934, 0.142, 0], [0.1934, -0.142, 0], [-0.1934, 0.142, 0], [-0.1934, -0.142, 0]])
+    yaw = rng.uniform(-np.pi, np.pi, B)
+    x = np.zeros((B, 12)); x[:, 0:2] = rng.uniform(-2, 2, (B, 2)); x[:, 2] = 0.27; x[:, 5] = yaw
+    R = records._rot_zyx(x[:, 3], x[:, 4], x[:, 5])
+    lever = np.zeros((B, 4, 3))
+    for leg in range(4):
+        lever[:, leg, 0] = np.cos(yaw) * so[leg, 0] - np.sin(yaw) * so[leg, 1]
+        lever[:, leg, 1] = np.sin(yaw) * so[leg, 0] + np.cos(yaw) * so[leg, 1]
+        lever[:, leg, 2] = -0.27
+    state = ct.RobotState(dev(x), dev(np.swapaxes(R, 1, 2).copy()), dev(lever), dev(np.full(B, records.GO2_MASS)),
+                          dev(np.einsum("bij,j,bkj->bik", R, records.GO2_I_BODY, R)))
+    cmd = np.stack([rng.uniform(-0.8, 0.8, B), rng.uniform(-0.4, 0.4, B), np.full(B, 0.27), rng.uniform(-2, 2, B)], axis=1)
+    cmd_d = [dev(cmd[:, i]) for i in range(4)]
+    traj = ct.ComTraj(state, hip_offset=hip, device="cuda:0")
+    traj.generate_traj(state, gait, 0.0, *cmd_d, dt)
+    mpc = mod.CentroidalMPC(None, traj, verbose=False)
+    for c in range(12):
+        pos_des_before = traj.pos_des_world.cpu().numpy().copy()
+        traj.generate_traj(state, gait, c * T, *cmd_d, dt)
+        sol = mpc.solve_QP(None, traj)
+        assert (sol["status"].cpu().numpy() == 1).all(), c
+        xs, Rs, ls = state.x.cpu().numpy(), state.R_world_to_body.cpu().numpy(), state.foot_lever_world.cpu().numpy()
+        xr, rf = traj.compute_x_ref_vec().cpu().numpy(), traj.r_foot.cpu().numpy()
+        for b in (0, 17, 95):       # the generated trajectory = the reference's generate_traj (oracle restatement)
+            pd, xr_o, rf_o = traj_ref.generate_traj(xs[b], Rs[b], ls[b], cmd[b], c * T, dt, N, HZ, DUTY, hip, pos_des_before[b])
+            assert np.abs(xr[b] - xr_o).max() < 1e-12 and np.abs(rf[b] - rf_o).max() < 1e-13
+            assert np.array_equal(rf[b] == 0, rf_o == 0)
+        u = mpc._u.cpu().numpy().reshape(B, 12 * N)
+        x2, R2, I2, l2 = records.srb_step_host(xs, u[:, :12], xr, rf, state.inertia.cpu().numpy(), state.mass.cpu().numpy(),
+                                               T, records.GO2_I_BODY, so)
+        state = ct.srb_step(state, traj, mpc._u, T, records.GO2_I_BODY, so)
+        for a, b_ in ((state.x, x2), (state.R_world_to_body, R2), (state.inertia, I2), (state.foot_lever_world, l2)):
+            assert np.abs(a.cpu().numpy() - b_).max() < 1e-11
+    rec = records.Records(xs, xr, rf, I2 * 0 + traj.I_com_world.cpu().numpy(), state.mass.cpu().numpy(),
+                          np.full(B, 11 * T), dt, HZ, DUTY, N)
+    for b in (3, 50):
+        o = oracle_solution(rec, b)
+        assert force_error(u[b], o["sol"]["U"])[1] < 1e-3
+    assert 0.2 < state.x[:, 2].mean().item() < 0.35           # still walking, not fallen through the floor
+
+
 def test_drop_in_single_robot_api(mod):
     """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
     rec = records.random_records(1, seed=9, stress=1.0)

@@ -165,3 +165,20 @@ def test_traj_generator_matches_reference_golden(emul):
         assert np.array_equal(rf == 0.0, g["r_foot"] == 0.0)                   # take-off / touch-down pattern: exact
         assert np.abs(xr - g["x_ref"]).max() <= 1e-13 * max(1.0, np.abs(g["x_ref"]).max())
         assert np.abs(rf - g["r_foot"]).max() <= 1e-14
+
+
+def test_srb_step_matches_numpy_twin(emul):
+    """csrc/cmpc_traj.cuh srb_step_one (host emulation) against records.srb_step_host."""
+    import ctypes
+    from helpers import _p
+    rec = records.random_records(64, seed=9, stress=0.3)
+    rng = np.random.default_rng(3)
+    u = rng.normal(0, 30, (rec.B, 12 * rec.N)); u[:, 2:12:3] = np.abs(u[:, 2:12:3]) + 20
+    so = np.array([[0.19, 0.14, 0], [0.19, -0.14, 0], [-0.19, 0.14, 0], [-0.19, -0.14, 0]], dtype=np.float64)
+    ib = np.array([0.11, 0.33, 0.38])
+    xo = np.zeros((rec.B, 12)); Rw = np.zeros((rec.B, 3, 3)); Io = np.zeros((rec.B, 3, 3)); lv = np.zeros((rec.B, 4, 3))
+    emul.lib.emul_srb_step(rec.N, rec.B, _p(rec.x0), _p(u), _p(rec.x_ref), _p(rec.r_foot), _p(rec.I_world), _p(rec.mass),
+                           ctypes.c_double(0.02), _p(ib), _p(so), _p(xo), _p(Rw), _p(Io), _p(lv))
+    x2, R2, I2, l2 = records.srb_step_host(rec.x0, u[:, :12], rec.x_ref, rec.r_foot, rec.I_world, rec.mass, 0.02, ib, so)
+    for a, b in ((xo, x2), (Rw, R2), (Io, I2), (lv, l2)):
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max())

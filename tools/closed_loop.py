@@ -1,0 +1,74 @@
+"""Device-resident closed loop (BASELINE configs[1] shape): B robots x C MPC cycles,
+    generate_traj -> contact table + solve_QP (warm-started) -> srb_step
+all on the GPU (cmpc_generate_traj, cmpc_contact_table, cmpc_solve, cmpc_srb_step); the host only enqueues.
+
+    python tools/closed_loop.py [B=1024] [cycles=500] [out=gpurun_out/closed_loop.json]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from convex_mpc_b200 import com_trajectory as ct, records  # noqa: E402
+from convex_mpc_b200.centroidal_mpc import CentroidalMPC  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+OUT = sys.argv[3] if len(sys.argv) > 3 else os.path.join("gpurun_out", "closed_loop.json")
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(1024)
+HZ, DUTY, N, MPC_DT = 3.0, 0.6, 16, 0.02
+gait = ct.Gait(HZ, DUTY)
+dt = gait.gait_period / N
+hip = np.array([[0.1934, 0.0465, 0], [0.1934, -0.0465, 0], [-0.1934, 0.0465, 0], [-0.1934, -0.0465, 0]])
+stance = np.array([[records.HIP_X, records.HIP_Y, 0], [records.HIP_X, -records.HIP_Y, 0],
+                   [-records.HIP_X, records.HIP_Y, 0], [-records.HIP_X, -records.HIP_Y, 0]])
+
+# start: standing at height 0.27 with random yaw, per-robot piecewise-constant commands (fwd / lateral / yaw rate)
+yaw = rng.uniform(-np.pi, np.pi, B)
+x = np.zeros((B, 12)); x[:, 0:2] = rng.uniform(-5, 5, (B, 2)); x[:, 2] = 0.27; x[:, 5] = yaw
+R = records._rot_zyx(x[:, 3], x[:, 4], x[:, 5])
+lever = np.zeros((B, 4, 3))
+for leg in range(4):
+    lever[:, leg, 0] = np.cos(yaw) * stance[leg, 0] - np.sin(yaw) * stance[leg, 1]
+    lever[:, leg, 1] = np.sin(yaw) * stance[leg, 0] + np.cos(yaw) * stance[leg, 1]
+    lever[:, leg, 2] = -0.27
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+state = ct.RobotState(t(x), t(np.swapaxes(R, 1, 2).copy()), t(lever), t(np.full(B, records.GO2_MASS)),
+                      t(np.einsum("bij,j,bkj->bik", R, records.GO2_I_BODY, R)))
+cmd = [t(rng.uniform(-0.8, 0.8, B)), t(rng.uniform(-0.4, 0.4, B)), t(np.full(B, 0.27)), t(rng.uniform(-2.0, 2.0, B))]
+
+traj = ct.ComTraj(state, hip_offset=hip, device=dev)
+traj.generate_traj(state, gait, 0.0, *cmd, dt)
+mpc = CentroidalMPC(None, traj, verbose=False, max_stance=40)
+nxt = None
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+solved = 0
+worst_rp = worst_rd = 0.0
+paths = np.zeros(4)
+WARM = 10
+for c in range(C + WARM):
+    if c == WARM:
+        torch.cuda.synchronize(); ev[0].record()
+    traj.generate_traj(state, gait, c * MPC_DT, *cmd, dt)
+    sol = mpc.solve_QP(None, traj)
+    nxt2 = ct.srb_step(state, traj, mpc._u, MPC_DT, records.GO2_I_BODY, stance, out=nxt)
+    state, nxt = nxt2, state
+    if c >= WARM and (c % 50 == 0 or c == C + WARM - 1):
+        st = sol["stats"].cpu().numpy()
+        solved += int((sol["status"].cpu().numpy() == 1).sum()); worst_rp = max(worst_rp, st[:, 0].max()); worst_rd = max(worst_rd, st[:, 1].max())
+        paths += np.bincount(st[:, 7].astype(int), minlength=4)[:4]
+ev[1].record(); torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1])
+xf = state.x.cpu().numpy()
+res = {"robots": B, "cycles": C, "ms_total": ms, "ms_per_cycle": ms / C, "cycles_per_s": C / ms * 1e3, "qps_per_s": B * C / ms * 1e3,
+       "checked_cycles_all_solved": bool(solved == B * (len(range(WARM, C + WARM, 50)) + (0 if (C + WARM - 1) % 50 == 0 else 1))),
+       "r_prim_max": worst_rp, "r_dual_max": worst_rd, "paths_sampled": paths.tolist(),
+       "height_mean": float(xf[:, 2].mean()), "height_min": float(xf[:, 2].min()), "speed_mean": float(np.linalg.norm(xf[:, 6:8], axis=1).mean()),
+       "note": "includes the Python enqueue overhead of three C-ABI calls + solution dict per cycle; one stream, no host sync inside the loop except every 50th cycle's status read"}
+os.makedirs(os.path.dirname(OUT) or ".", exist_ok=True)
+json.dump(res, open(OUT, "w"), indent=1)
+print(json.dumps(res))
