@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--stress", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--prepass", action="store_true", help="Riccati pre-pass ahead of the condensed kernel (A/B timing)")
+    ap.add_argument("--prepass", type=int, default=0, help="Riccati pre-pass ahead of the condensed kernel: 0 off, 1 v1, 2 v2 (A/B timing)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep 1..262144 -> gpurun_out/sweep.json")
     return ap.parse_args()
 

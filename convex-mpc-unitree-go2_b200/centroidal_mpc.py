@@ -180,7 +180,7 @@ class CentroidalMPC:
             check(self._lib.cmpc_set_max_stance(self._h, int(max_stance)))
         if generic_kernel:
             check(self._lib.cmpc_set_generic(self._h, 1))
-        check(self._lib.cmpc_set_prepass(self._h, 1 if prepass else 0))
+        check(self._lib.cmpc_set_prepass(self._h, int(prepass)))
         self._state_B = None
         self._warm = False
         self._warm_host = 0

@@ -22,6 +22,7 @@
 #include "cmpc_core.cuh"
 #include "cmpc_fast.cuh"
 #include "cmpc_riccati.cuh"
+#include "cmpc_riccati2.cuh"
 #include "cmpc_traj.cuh"
 
 using namespace cmpc;
@@ -224,6 +225,30 @@ riccati_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, do
         const int done = ric::riccati_one(c, p, in, o, w, nfmax, warm, g);
         if (!done && lane == 0) worklist[atomicAdd(wl_count, 1)] = b;
         __syncwarp();
+    }
+}
+
+// Pre-pass, version 2 (cmpc_riccati2.cuh): two robots per warp, register-resident rows.
+constexpr int kRic2Threads = 64;
+__global__ void __launch_bounds__(kRic2Threads)
+riccati2_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* __restrict__ gains,
+                size_t gain_stride, int* __restrict__ worklist, int* __restrict__ wl_count, size_t smem_per_half) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    const int hpb = (blockDim.x >> 5) * 2;                       // robots in flight per block
+    const int slot = wid * 2 + half;
+    ric2::WsH w;
+    ric2::carve_half(w, smem + (size_t)slot * smem_per_half, bi.N);
+    const int gh = blockIdx.x * hpb + slot, nh = gridDim.x * hpb;
+    double* g = gains + (size_t)gh * gain_stride;
+    const int N = bi.N;
+    for (int b = gh; b < B; b += nh) {
+        QpIn in = qp_in(bi, b);
+        QpOut o = qp_out(bo, b, N);
+        const int done = ric2::riccati_half(hmask, hl, p, in, o, w, nfmax, warm, g);
+        if (!done && hl == 0) worklist[atomicAdd(wl_count, 1)] = b;
+        __syncwarp(hmask);
     }
 }
 
@@ -554,7 +579,7 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
 
 int cmpc_set_prepass(cmpc_handle* h, int on) {
     if (!h) return fail("null handle");
-    h->prepass = on ? 1 : 0;
+    h->prepass = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 reference sweep (one robot per warp), 2 register-resident sweep
     return 0;
 }
 
@@ -710,17 +735,29 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                     ps.cap = B;
                 }
                 if (!ps.count) CU_TRY(cudaMalloc(&ps.count, sizeof(int)));
-                const size_t need_g = gd * (size_t)h->sm_count * 3 * wpb;
+                const size_t need_g = gd * (size_t)h->sm_count * 32;          // up to 32 robots in flight per SM (v2)
                 if (ps.gain_doubles < need_g) {
                     if (ps.gains) cudaFree(ps.gains);
                     ps.gains = nullptr;
                     CU_TRY(cudaMalloc(&ps.gains, need_g * sizeof(double)));
                     ps.gain_doubles = need_g;
                 }
-                CU_TRY(cudaFuncSetAttribute((const void*)riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
                 CU_TRY(cudaMemsetAsync(ps.count, 0, sizeof(int), (cudaStream_t)stream));
-                riccati_kernel<<<grid_r, kRicThreads, smem_r, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd,
-                                                                                  ps.worklist, ps.count, per_warp);
+                const size_t per_half = ric2::half_bytes(h->N);
+                const int hpb = (kRic2Threads / 32) * 2;
+                const size_t smem_2 = per_half * hpb;
+                int per_sm2 = (int)(h->smem_per_sm / (smem_2 + 1024));
+                if (per_sm2 > 8) per_sm2 = 8;
+                if (h->prepass == 2 && per_sm2 >= 1 && gd * (size_t)h->sm_count * per_sm2 * hpb <= ps.gain_doubles) {
+                    const int want2 = (B + hpb - 1) / hpb, cap2 = h->sm_count * per_sm2;
+                    CU_TRY(cudaFuncSetAttribute((const void*)riccati2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2));
+                    riccati2_kernel<<<want2 < cap2 ? want2 : cap2, kRic2Threads, smem_2, (cudaStream_t)stream>>>(
+                        h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd, ps.worklist, ps.count, per_half);
+                } else {
+                    CU_TRY(cudaFuncSetAttribute((const void*)riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                    riccati_kernel<<<grid_r, kRicThreads, smem_r, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd,
+                                                                                      ps.worklist, ps.count, per_warp);
+                }
                 ++g_launches;
                 CU_TRY(cudaGetLastError());
                 wl = ps.worklist; wlc = ps.count;

@@ -171,11 +171,12 @@ def test_forces_match_exact_optimum(mod, stress, B):
     assert worst < 1e-6        # in practice the active-set path is exact to ~1e-9 N
 
 
-def test_riccati_prepass_same_optimum(mod):
+@pytest.mark.parametrize("version", [1, 2])
+def test_riccati_prepass_same_optimum(mod, version):
     """cmpc_set_prepass(1): warp-per-robot Riccati sweep + device work-list for the rest.  Same statuses, paths
     and forces as the condensed kernel alone, forces within tolerance of the oracle's exact optimum."""
     rec = records.random_records(2048, seed=611, stress=0.3)
-    a, traj = make_mpc(mod, rec, prepass=True, max_stance=40)
+    a, traj = make_mpc(mod, rec, prepass=version, max_stance=40)
     b, _ = make_mpc(mod, rec, max_stance=40)
     sa, sb = a.solve_QP(None, traj), b.solve_QP(None, traj)
     ua, ub = sa["u"].cpu().numpy(), sb["u"].cpu().numpy()
