@@ -292,6 +292,15 @@ def main():
         hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 (of fallback)"
         ach_tf = flops / (kms * 1e-3) / 1e12
         alg_bytes = roofline.bytes_per_qp(N) * B
+        # DRAM traffic per launch from the committed ncu capture of the same kernel (per-robot figure x robots)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_v3_dram_traffic.json")))
+            if N == 16 and args.mode == "active_set":
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["robots"] * B
+                traffic_src = "profiles/r01_v3_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled per robot)"
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "p50_batch_ms": float(np.median(per_step)),
@@ -304,8 +313,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "CentroidalMPC.solve_host -> cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64_fma", "kernel": "solve_kernel", "achieved": ach_tf, "peak": f64.value,
-                         "unit": "TFLOP/s", "frac": ach_tf / f64.value, "traffic": None,
+            "roofline": {"bound": "fp64_fma", "kernel": "solve_fast_kernel", "achieved": ach_tf, "peak": f64.value,
+                         "unit": "TFLOP/s", "frac": ach_tf / f64.value, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_ms": kms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "cmpc_microbench DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "smem_gbs_measured": smem.value,
