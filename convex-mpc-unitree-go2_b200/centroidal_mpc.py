@@ -390,6 +390,31 @@ class CentroidalMPC:
         return sol
 
     # ------------------------------------------------------------------------------------------
+    def enqueue(self, traj, stream=None):
+        """Asynchronous variant of ``solve_QP`` for device-resident loops: enqueue the contact table and the fused
+        solve of one cycle on ``stream`` (default: torch's current stream) and return at once -- no host
+        synchronisation, no events, no solution dict, so the call can be captured in a CUDA graph
+        (tools/closed_loop.py).  Results land in ``self._u`` (B, 12N: forces, entries 0..11 = step 0), ``self._X``,
+        ``self._y``, ``self._nu``, ``self._status``, ``self._iters``, ``self._stats``; tensors of ``traj`` must stay
+        alive until the stream has run."""
+        B = max(self._batch_of(traj), 1)
+        if int(traj.N) != self.N:
+            raise _lib.CmpcError(f"traj.N = {traj.N} but the solver was built for N = {self.N}")
+        self._alloc_state(B)
+        with torch.cuda.device(self.device):
+            s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+            t, _ = self._gather(traj, B, s)
+            p = lambda k: t[k].data_ptr() if k in t else None
+            check(self._lib.cmpc_solve(
+                self._h, B, p("Ad"), p("Bd"), p("gd"), p("x0"), p("x_ref"), p("r_foot"), p("I_world"), p("mass"),
+                float(t.get("dt", 0.0)), self._mask.data_ptr(), int(self._warm),
+                self._u.data_ptr(), self._y.data_ptr(), self._rho.data_ptr(), self._X.data_ptr(),
+                self._nu.data_ptr(), self._status.data_ptr(), self._iters.data_ptr(), self._stats.data_ptr(), s))
+        self._keep = t
+        if OPTS.get("warm_start_primal", True):
+            self._warm = True
+
+    # ------------------------------------------------------------------------------------------
     def solve_host(self, x0, x_ref, r_foot, I_world, mass, t0, dt, gait_hz=3.0, duty=0.6,
                    phase_offset=PHASE_OFFSET, out=None):
         """Whole cycle on HOST buffers through ``cmpc_solve_host`` (chunked, copy/compute overlapped).

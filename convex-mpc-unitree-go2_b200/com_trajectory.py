@@ -97,11 +97,34 @@ class ComTraj(BatchedComTraj):
                 _lib.darr(self.hip_offset.reshape(-1)), self.pos_des_world.data_ptr(), self.pos_des_world.data_ptr(),
                 self._x_ref_buf.data_ptr(), self._r_foot_buf.data_ptr(), ctypes.c_void_p(s)))
         self._keep = (x0, R_wb, lever, cmd, t0)                    # inputs stay alive until the stream has run
+        self._set_fields(N, x0, state, t0, time_step, gait)
+        return self
+
+    def enqueue_generate(self, state, gait, t0, cmd, time_step, stream=None):
+        """Lean variant of ``generate_traj`` for device-resident loops / CUDA-graph capture: ``t0`` (B,) and ``cmd``
+        (B,4) = [vx_body, vy_body, z_des, yaw_rate] are device tensors the caller owns, ``state`` holds contiguous
+        FP64 device tensors; no temporaries are created once the output buffers exist."""
+        B, dev = self.B, self.device
+        N = int(gait.gait_period / time_step)
+        if self.N != N or not hasattr(self, "_x_ref_buf"):
+            self._x_ref_buf = torch.empty(B, 12, N, dtype=torch.float64, device=dev)
+            self._r_foot_buf = torch.empty(B, 4, 3, N, dtype=torch.float64, device=dev)
+        s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.cmpc_generate_traj(
+                dev.index or 0, N, B, state.x.data_ptr(), state.R_world_to_body.data_ptr(), state.foot_lever_world.data_ptr(),
+                cmd.data_ptr(), t0.data_ptr(), float(time_step), float(gait.gait_hz), float(gait.gait_duty),
+                _lib.darr(self.phase_offset), _lib.darr(self.hip_offset.reshape(-1)), self.pos_des_world.data_ptr(),
+                self.pos_des_world.data_ptr(), self._x_ref_buf.data_ptr(), self._r_foot_buf.data_ptr(), ctypes.c_void_p(s)))
+        self._set_fields(N, state.x, state, t0, time_step, gait)
+        return self
+
+    def _set_fields(self, N, x0, state, t0, time_step, gait):
+        dev, B = self.device, self.B
         BatchedComTraj.__init__(self, N, x0, self._x_ref_buf, time_step, m=_dev(state.mass, dev, (B,)),
                                 I_com_world=_dev(state.inertia, dev, (B, 3, 3)), r_foot=self._r_foot_buf,
                                 time_now=t0, gait_hz=gait.gait_hz, gait_duty=gait.gait_duty,
                                 phase_offset=self.phase_offset)
-        return self
 
 
 def srb_step(state, traj, u, mpc_period, I_body, stance_offset, out=None, stream=None):

@@ -285,6 +285,35 @@ def test_device_resident_closed_loop(mod):
     assert 0.2 < state.x[:, 2].mean().item() < 0.35           # still walking, not fallen through the floor
 
 
+def test_enqueue_and_cuda_graph_replay_equal_solve_QP(mod):
+    """CentroidalMPC.enqueue (no host synchronisation) gives solve_QP's results, eagerly and replayed from a CUDA
+    graph (the capture path tools/closed_loop.py uses)."""
+    rec = records.random_records(512, seed=91, stress=0.3)
+    a, traj = make_mpc(mod, rec, max_stance=40)
+    ref = a.solve_QP(None, traj)["u"].cpu().numpy().copy()
+    b, _ = make_mpc(mod, rec, max_stance=40)
+    b.enqueue(traj)
+    torch.cuda.synchronize()
+    assert np.array_equal(b._u.view(512, 16, 12).transpose(1, 2).cpu().numpy(), ref)
+    c, _ = make_mpc(mod, rec, max_stance=40)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        c.enqueue(traj)                  # warm-up: allocations happen outside the capture
+        c.reset()
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            c.enqueue(traj)
+        c._u.zero_()
+        c._rho.zero_()
+        g.replay()
+        side.synchronize()
+    assert (c._status.cpu().numpy() == 1).all()
+    exact = c._stats.cpu().numpy()[:, 7] < 2
+    assert np.abs(c._u.view(512, 16, 12).transpose(1, 2).cpu().numpy() - ref)[exact].max() < 1e-7
+
+
 def test_drop_in_single_robot_api(mod):
     """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
     rec = records.random_records(1, seed=9, stress=1.0)
