@@ -87,3 +87,44 @@ def test_sparse_structure_counts():
         assert (lbx[3 * leg + 2, ~swing[leg]] == 10).all()
         assert np.isinf(ubx[3 * leg + 2, ~swing[leg]]).all()
         assert np.isinf(lbx[3 * leg, ~swing[leg]]).all()
+
+
+def test_exact_optimum_agrees_with_scipy_slsqp():
+    """Third-party cross-check of the oracle's optimum (the CasADi -> OSQP binary of centroidal_mpc.py:98 cannot be
+    installed here): SciPy's SLSQP, an independent QP/NLP code, solves the same condensed QP over the stance forces
+    -- with active friction / fz_min rows -- to the same point (<= 1e-3 N, far inside the 1e-2 N parity budget) and
+    the same objective."""
+    from scipy.optimize import minimize
+    from convex_mpc_b200 import records
+    from helpers import oracle_solution
+    rec = records.random_records(8, seed=5, stress=0.5)
+    n_active_seen = 0
+    for b in (4, 5):
+        o = oracle_solution(rec, b)
+        cq = o["cq"]
+        H, g, A, l, u = cq["H"], cq["g"], cq["A"], cq["l"], cq["u"]
+        n = H.shape[0]
+        free = np.flatnonzero(~((l[:n] == 0) & (u[:n] == 0)))           # swing forces are pinned to zero
+        Hf, gf = H[np.ix_(free, free)], g[free]
+        rows, rhs = [], []
+        for i, j in enumerate(free):
+            if np.isfinite(l[j]):
+                e = np.zeros(len(free)); e[i] = 1.0
+                rows.append(e); rhs.append(l[j])                        # fz >= fz_min
+        F, fu = A[n:][:, free], u[n:]
+        for r in np.flatnonzero(np.isfinite(fu)):
+            rows.append(-F[r]); rhs.append(-fu[r])                      # pyramid face <= 0
+        G, hv = np.array(rows), np.array(rhs)
+        sc = 1.0 / np.abs(Hf).max()
+        x0 = np.zeros(len(free)); x0[2::3] = 40.0
+        res = minimize(lambda x: sc * (0.5 * x @ Hf @ x + gf @ x), x0, jac=lambda x: sc * (Hf @ x + gf), method="SLSQP",
+                       constraints=[dict(type="ineq", fun=lambda x: G @ x - hv, jac=lambda x: G)],
+                       options=dict(ftol=1e-16, maxiter=2000))
+        assert res.status == 0
+        U = np.zeros(n); U[free] = res.x
+        Us = o["sol"]["U"]
+        assert np.abs(U - Us).max() < 1e-3
+        obj = lambda v: 0.5 * v @ H @ v + g @ v
+        assert abs(obj(U) - obj(Us)) < 1e-8 * max(1.0, abs(obj(Us)))
+        n_active_seen += int((np.abs(G @ Us[free] - hv) < 1e-7).sum())
+    assert n_active_seen > 0            # the cases do exercise active constraints
