@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--stress", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--prepass", type=int, default=0, help="Riccati pre-pass ahead of the condensed kernel: 0 off, 1 v1, 2 v2 (A/B timing)")
+    ap.add_argument("--prepass", type=int, default=3, help="Riccati pre-pass ahead of the condensed kernel: 0 off, 1 v1, 2 v2, 3 v2 lock-step (default)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep 1..262144 -> gpurun_out/sweep.json")
     return ap.parse_args()
 
@@ -249,6 +249,7 @@ def main():
     iters = mpc._iters.cpu().numpy()
     stats = mpc._stats.cpu().numpy()
     flops = roofline.batch_flops(stats, iters, N)
+    flops_route = roofline.batch_flops(stats, iters, N, route_actual=True)
     kms = float(np.mean(kern_ms))
 
     # ---- end-to-end through the host-buffer C-ABI call ------------------------------------------
@@ -276,7 +277,7 @@ def main():
     assert (out[1].numpy() == status).all()
 
     # ---- statistics gathered across ranks (the only collective of the run) ----------------------
-    recs = sharding.gather_stats(sharding.local_stats(status, iters, stats, total_ms, flops), device=dev)
+    recs = sharding.gather_stats(sharding.local_stats(status, iters, stats, total_ms, flops, flops_route), device=dev)
     summ = sharding.reduce_stats(recs)
 
     line = None
@@ -316,13 +317,17 @@ def main():
             "roofline": {"bound": "fp64_fma", "kernel": "solve_fast_kernel", "achieved": ach_tf, "peak": f64.value,
                          "unit": "TFLOP/s", "frac": ach_tf / f64.value, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_ms": kms, "algorithmic_flops_per_launch": flops,
+                         "frac_route_actual": flops_route / (kms * 1e-3) / 1e12 / f64.value,
+                         "note": "frac counts every robot at the condensed route's flops (SURVEY 8d per-unit figure); "
+                                 "frac_route_actual counts robots finished by the Riccati pre-pass at that sweep's (4.5x smaller) flops; "
+                                 "kernel_ms = pre-pass + condensed kernel of one cmpc_solve call",
                          "peak_source": "cmpc_microbench DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "smem_gbs_measured": smem.value,
                          "hbm": {"achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic_bytes_per_launch": alg_bytes}},
             "solver": {k: summ[k] for k in ("solved", "max_iter", "inaccurate", "failed", "path_unconstrained",
-                                            "path_active_set", "path_admm", "path_admm_polish", "r_prim_max", "r_dual_max")},
+                                            "path_active_set", "path_admm", "path_admm_polish", "path_riccati", "r_prim_max", "r_dual_max")},
         }
         line["solver"]["as_iters_mean"] = summ["as_iters_sum"] / max(summ["qps_count"], 1)
         line["solver"]["n_free_mean"] = summ["n_free_sum"] / max(summ["qps_count"], 1)

@@ -246,8 +246,35 @@ riccati2_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, d
     for (int b = gh; b < B; b += nh) {
         QpIn in = qp_in(bi, b);
         QpOut o = qp_out(bo, b, N);
-        const int done = ric2::riccati_half(hmask, hl, p, in, o, w, nfmax, warm, g);
+        const int done = ric2::riccati_half<false>(hmask, hl, true, p, in, o, w, nfmax, warm, g);
         if (!done && hl == 0) worklist[atomicAdd(wl_count, 1)] = b;
+        __syncwarp(hmask);
+    }
+}
+
+// The same sweep with the sixteen robots of a 256-thread CTA in lock-step (one CTA barrier per stage).
+constexpr int kRic2LsThreads = 256;
+__global__ void __launch_bounds__(kRic2LsThreads, 1)
+riccati2_lockstep_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* __restrict__ gains,
+                         size_t gain_stride, int* __restrict__ worklist, int* __restrict__ wl_count, size_t smem_per_half) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    const int hpb = (blockDim.x >> 5) * 2;
+    const int slot = wid * 2 + half;
+    ric2::WsH w;
+    ric2::carve_half(w, smem + (size_t)slot * smem_per_half, bi.N);
+    const int gh = blockIdx.x * hpb + slot, nh = gridDim.x * hpb;
+    double* g = gains + (size_t)gh * gain_stride;
+    const int N = bi.N;
+    const int rounds = (B + nh - 1) / nh;
+    for (int it = 0; it < rounds; ++it) {
+        const int b = gh + it * nh;
+        const bool valid = b < B;
+        QpIn in = qp_in(bi, valid ? b : 0);
+        QpOut o = qp_out(bo, valid ? b : 0, N);
+        const int done = ric2::riccati_half<true>(hmask, hl, valid, p, in, o, w, nfmax, warm, g);
+        if (done == 0 && hl == 0) worklist[atomicAdd(wl_count, 1)] = b;
         __syncwarp(hmask);
     }
 }
@@ -397,7 +424,7 @@ struct cmpc_handle {
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     Params p;
-    int prepass = 0;       // Riccati pre-pass ahead of the condensed kernel (active-set mode, raw inputs); opt-in
+    int prepass = 3;       // Riccati pre-pass ahead of the condensed kernel (active-set mode, raw inputs): 0 off, 1 v1, 2 v2, 3 v2 lock-step
     // pre-pass slots (work-list, its counter, gain scratch); calls rotate over them so that solves enqueued on
     // different streams do not share one
     struct PreSlot { int* worklist = nullptr; int* count = nullptr; double* gains = nullptr; int cap = 0; size_t gain_doubles = 0; };
@@ -579,7 +606,7 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
 
 int cmpc_set_prepass(cmpc_handle* h, int on) {
     if (!h) return fail("null handle");
-    h->prepass = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 off, 1 reference sweep (one robot per warp), 2 register-resident sweep
+    h->prepass = on < 0 ? 0 : (on > 3 ? 3 : on);      // 0 off, 1 reference sweep (one robot per warp), 2 register-resident sweep, 3 = 2 in lock-step
     return 0;
 }
 
@@ -726,29 +753,40 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 if (per_sm < 1) per_sm = 1;
                 const int want = (B + wpb - 1) / wpb, cap = h->sm_count * per_sm;
                 const int grid_r = want < cap ? want : cap;
-                auto& ps = h->pre[h->pre_next++ & 3u];
                 const size_t gd = ric::gain_doubles(h->nfmax);
-                if (ps.cap < B) {
-                    if (ps.worklist) cudaFree(ps.worklist);
-                    ps.worklist = nullptr;
-                    CU_TRY(cudaMalloc(&ps.worklist, (size_t)B * sizeof(int)));
-                    ps.cap = B;
-                }
-                if (!ps.count) CU_TRY(cudaMalloc(&ps.count, sizeof(int)));
                 const size_t need_g = gd * (size_t)h->sm_count * 32;          // up to 32 robots in flight per SM (v2)
-                if (ps.gain_doubles < need_g) {
-                    if (ps.gains) cudaFree(ps.gains);
-                    ps.gains = nullptr;
-                    CU_TRY(cudaMalloc(&ps.gains, need_g * sizeof(double)));
-                    ps.gain_doubles = need_g;
+                // all four slots are (re)sized together, on the first call that needs it: later calls -- including
+                // calls made while a CUDA graph is being captured -- allocate nothing
+                for (auto& q : h->pre) {
+                    if (q.cap < B) {
+                        if (q.worklist) cudaFree(q.worklist);
+                        q.worklist = nullptr;
+                        CU_TRY(cudaMalloc(&q.worklist, (size_t)B * sizeof(int)));
+                        q.cap = B;
+                    }
+                    if (!q.count) CU_TRY(cudaMalloc(&q.count, sizeof(int)));
+                    if (q.gain_doubles < need_g) {
+                        if (q.gains) cudaFree(q.gains);
+                        q.gains = nullptr;
+                        CU_TRY(cudaMalloc(&q.gains, need_g * sizeof(double)));
+                        q.gain_doubles = need_g;
+                    }
                 }
+                auto& ps = h->pre[h->pre_next++ & 3u];
                 CU_TRY(cudaMemsetAsync(ps.count, 0, sizeof(int), (cudaStream_t)stream));
                 const size_t per_half = ric2::half_bytes(h->N);
                 const int hpb = (kRic2Threads / 32) * 2;
                 const size_t smem_2 = per_half * hpb;
                 int per_sm2 = (int)(h->smem_per_sm / (smem_2 + 1024));
                 if (per_sm2 > 8) per_sm2 = 8;
-                if (h->prepass == 2 && per_sm2 >= 1 && gd * (size_t)h->sm_count * per_sm2 * hpb <= ps.gain_doubles) {
+                const size_t smem_ls = per_half * (kRic2LsThreads / 32) * 2;
+                if (h->prepass == 3 && smem_ls <= h->smem_optin) {
+                    const int hpl = (kRic2LsThreads / 32) * 2;
+                    const int want3 = (B + hpl - 1) / hpl;
+                    CU_TRY(cudaFuncSetAttribute((const void*)riccati2_lockstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ls));
+                    riccati2_lockstep_kernel<<<want3 < h->sm_count ? want3 : h->sm_count, kRic2LsThreads, smem_ls, (cudaStream_t)stream>>>(
+                        h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd, ps.worklist, ps.count, per_half);
+                } else if (h->prepass >= 2 && per_sm2 >= 1 && gd * (size_t)h->sm_count * per_sm2 * hpb <= ps.gain_doubles) {
                     const int want2 = (B + hpb - 1) / hpb, cap2 = h->sm_count * per_sm2;
                     CU_TRY(cudaFuncSetAttribute((const void*)riccati2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2));
                     riccati2_kernel<<<want2 < cap2 ? want2 : cap2, kRic2Threads, smem_2, (cudaStream_t)stream>>>(

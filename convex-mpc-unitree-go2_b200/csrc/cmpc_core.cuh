@@ -64,7 +64,7 @@ struct Params {
 
 // status / path codes (mirrors include/cmpc.h)
 enum { ST_SOLVED = 1, ST_INACCURATE = 2, ST_MAX_ITER = -2, ST_NON_CVX = -7, ST_TOO_MANY_FEET = -20 };
-enum { PATH_UNCONSTRAINED = 0, PATH_ACTIVE_SET = 1, PATH_ADMM = 2, PATH_ADMM_POLISH = 3 };
+enum { PATH_UNCONSTRAINED = 0, PATH_ACTIVE_SET = 1, PATH_ADMM = 2, PATH_ADMM_POLISH = 3, PATH_RICCATI = 4 };
 enum { NSTAT = 8 };
 
 // Shared-memory workspace of one CTA (all pointers into one dynamic smem allocation).

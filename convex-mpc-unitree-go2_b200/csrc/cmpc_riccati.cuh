@@ -436,7 +436,7 @@ CMPC_HD int riccati_one(const Cta& c, const Params& p, const QpIn& in, QpOut& o,
         o.stats[4] = 0.0;
         o.stats[5] = rho;
         o.stats[6] = 0.0;
-        o.stats[7] = (double)PATH_UNCONSTRAINED;
+        o.stats[7] = (double)PATH_RICCATI;
     }
     return 1;
 }

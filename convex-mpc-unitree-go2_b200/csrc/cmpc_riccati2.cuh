@@ -20,6 +20,10 @@ namespace ric2 {
 
 constexpr int LD = 14;
 constexpr int MAT = 12 * LD;
+#ifndef CMPC_RIC_SYNC_EVERY
+#define CMPC_RIC_SYNC_EVERY 8     // lock-step granularity: one CTA barrier every this many stages (measured: 1 -> 10.4 ms,
+                                  // 2 -> 10.0, 4 -> 9.7, 8 / 16 / once per sweep -> 9.4 ms per 65 536 robots)
+#endif
 
 struct WsH {          // shared memory of one robot (half-warp)
     double* RF;       // 12N lever arms, index (leg*3 + a)*N + k
@@ -329,16 +333,22 @@ __device__ __forceinline__ void back_stage(unsigned hmask, int hl, int i, bool a
     }
 
 // One robot on one half-warp.  Returns 1 if finished here (outputs written), 0 if it goes on to the condensed path.
-__device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params& p, const QpIn& in, QpOut& o, WsH& w,
-                                            int nfmax, int warm, double* gains) {
+// LS (lock-step): the halves of a CTA meet at a CTA barrier before every backward stage and forward step, so that
+// they run the same stretch of code at the same time and share fetched instruction lines (the sweep is
+// instruction-fetch bound).  Every half then has to reach every barrier: early exits become `alive = false`, and
+// halves without a robot (valid == false) walk through the loops idle.  Returns -1 for those.
+template <bool LS>
+__device__ __forceinline__ int riccati_half(unsigned hmask, int hl, bool valid, const Params& p, const QpIn& in, QpOut& o,
+                                            WsH& w, int nfmax, int warm, double* gains) {
     const int N = in.N;
     const int W = (4 * N + 63) >> 6;
-    const unsigned long long mk0 = in.mask ? in.mask[0] : ~0ull, mk1 = (in.mask && W > 1) ? in.mask[1] : ~0ull,
-                             mk2 = (in.mask && W > 2) ? in.mask[2] : ~0ull;
+    bool alive = valid;
+    const unsigned long long mk0 = (alive && in.mask) ? in.mask[0] : ~0ull, mk1 = (alive && in.mask && W > 1) ? in.mask[1] : ~0ull,
+                             mk2 = (alive && in.mask && W > 2) ? in.mask[2] : ~0ull;
     const int i = hl < 12 ? hl : 11;            // lanes 12..15 shadow row 11 (reads stay in bounds, writes are masked)
     const bool act = hl < 12;
     // ---- set-up
-    if (hl == 0) {
+    if (alive && hl == 0) {
         DynCommon dc;
         dyn_common(dc, in.x_ref, N, in.I_world, in.mass, in.dt);
         w.dynv[0] = dc.cy; w.dynv[1] = dc.sy;
@@ -351,15 +361,15 @@ __device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params
         }
         w.vstart[N] = 3 * nf;
     }
-    for (int idx = hl; idx < 12 * N; idx += 16) {
+    for (int idx = hl; alive && idx < 12 * N; idx += 16) {
         const int r = idx / N, c = idx - r * N;
         w.XR[c * 12 + r] = in.x_ref[idx];
         w.RF[idx] = in.r_foot[idx];
         w.U[idx] = 0.0;
     }
     __syncwarp(hmask);
-    const int n = w.vstart[N];
-    if (n > 3 * nfmax || n == 0) return 0;
+    const int n = alive ? w.vstart[N] : 0;
+    if (n > 3 * nfmax || n == 0) { if (!LS) return 0; alive = false; }
     Dyn d;
     d.cy = w.dynv[0]; d.sy = w.dynv[1]; d.minv = w.dynv[11]; d.dt = in.dt; d.h = in.dt * in.dt / 2.0;
     const double gz2 = -9.81 * d.h, gz8 = -9.81 * d.dt;
@@ -381,6 +391,8 @@ __device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params
     double pvi = -Qi * w.XR[(N - 1) * 12 + i];
     double pmin = 1.0;
     for (int k = N - 1; k >= 0; --k) {
+        if (LS && ((N - 1 - k) % CMPC_RIC_SYNC_EVERY) == 0) __syncthreads();
+        if (!alive) continue;
         int legs[4] = {0, 0, 0, 0};
         int cnt = 0;
 #pragma unroll
@@ -390,18 +402,19 @@ __device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params
                 ++cnt;
             }
         const int m = 3 * cnt;
-        const int voff_unused = 0; (void)voff_unused;
         if (cnt == 2) back_stage<6>(hmask, hl, i, act, p, w, d, N, k, m, legs, Pr, pvi, pmin, Kst, kst, ra, rb, ca, cb, Qi, gz2, gz8);
         else if (cnt == 4) back_stage<12>(hmask, hl, i, act, p, w, d, N, k, m, legs, Pr, pvi, pmin, Kst, kst, ra, rb, ca, cb, Qi, gz2, gz8);
         else back_stage<0>(hmask, hl, i, act, p, w, d, N, k, m, legs, Pr, pvi, pmin, Kst, kst, ra, rb, ca, cb, Qi, gz2, gz8);
     }
     pmin = -max16(hmask, -pmin);
-    if (!(pmin > 0.0)) return 0;
+    if (!(pmin > 0.0)) { if (!LS) return 0; alive = false; }
     __syncwarp(hmask);
 
     // ---- forward sweep
-    double xi = in.x0[i];
+    double xi = alive ? in.x0[i] : 0.0;
     for (int k = 0; k < N; ++k) {
+        if (LS && (k % CMPC_RIC_SYNC_EVERY) == 0) __syncthreads();
+        if (!alive) continue;
         int legs[4] = {0, 0, 0, 0};
         int cnt = 0;
 #pragma unroll
@@ -461,6 +474,8 @@ __device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params
         xi = xn;
         __syncwarp(hmask);
     }
+
+    if (!alive) return valid ? 0 : -1;
 
     // ---- feasibility of the unconstrained minimiser
     double mv = -1e300;
@@ -547,7 +562,7 @@ __device__ __forceinline__ int riccati_half(unsigned hmask, int hl, const Params
         o.stats[4] = 0.0;
         o.stats[5] = rho;
         o.stats[6] = 0.0;
-        o.stats[7] = (double)PATH_UNCONSTRAINED;
+        o.stats[7] = (double)PATH_RICCATI;
     }
     return 1;
 }

@@ -33,13 +33,31 @@ def flops_per_qp(n, path, as_iters, n_active, admm_iters, nfac, N=16):
     return f
 
 
-def batch_flops(stats, iters, N=16):
-    """Total algorithmic flops of a batch from the (B, NSTAT) stats array and the ADMM iteration counts."""
+def riccati_flops_per_qp(n, N=16):
+    """Work of the Riccati pre-pass (csrc/cmpc_riccati*.cuh) for a robot with n stance variables over N stages,
+    taking m = n/N variables per stage (convexity makes this a slight under-count):
+    per stage  P B 288 m, B'PB 24 m^2, Cholesky + inverse 2 m^3/3, Y = W S and K = W'Y 24 m^2, A'PA 576,
+    S'K 288 m, vectors 72 m;  forward sweep 48 n + 24 N;  epilogue as the condensed route."""
+    n = np.asarray(n, dtype=np.float64)
+    m = n / N
+    stage = 2 * m ** 3 / 3 + 48 * m ** 2 + 648 * m + 576
+    return N * stage + 48 * n + 24 * N + 2 * (2 * 144 * N + 24 * n) + 4 * n
+
+
+def batch_flops(stats, iters, N=16, route_actual=False):
+    """Total algorithmic flops of a batch from the (B, NSTAT) stats array and the ADMM iteration counts.
+    Robots finished by the Riccati pre-pass (path 4) count at the condensed route's figure for an unconstrained
+    robot -- the per-unit figure of SURVEY.md section 8(d), comparable across kernel versions -- unless
+    ``route_actual`` asks for the flops of the route they really took."""
     stats = np.asarray(stats)
     path = stats[:, 7].astype(np.int64)
+    ric = path == 4
+    path = np.where(ric, 0, path)
     admm = (path >= 2)
-    return float(flops_per_qp(stats[:, 3], path, stats[:, 6], stats[:, 4], np.asarray(iters) * admm,
-                              admm.astype(np.float64), N).sum())
+    f = flops_per_qp(stats[:, 3], path, stats[:, 6], stats[:, 4], np.asarray(iters) * admm, admm.astype(np.float64), N)
+    if route_actual:
+        f = np.where(ric, riccati_flops_per_qp(stats[:, 3], N), f)
+    return float(f.sum())
 
 
 def bytes_per_qp(N=16):

@@ -8,7 +8,7 @@ import numpy as np
 
 STAT_FIELDS = ("qps_count", "elapsed_ms", "solved", "max_iter", "inaccurate", "failed",
                "path_unconstrained", "path_active_set", "path_admm", "path_admm_polish",
-               "as_iters_sum", "admm_iters_sum", "n_free_sum", "r_prim_max", "r_dual_max", "flops")
+               "as_iters_sum", "admm_iters_sum", "n_free_sum", "r_prim_max", "r_dual_max", "flops", "path_riccati", "flops_route")
 
 
 def env_rank_world():
@@ -23,7 +23,7 @@ def shard_range(B, rank, world):
     return min(rank * per, B), min((rank + 1) * per, B)
 
 
-def local_stats(status, iters, stats, elapsed_ms, flops=0.0):
+def local_stats(status, iters, stats, elapsed_ms, flops=0.0, flops_route=0.0):
     """Fixed-size float64 record (len(STAT_FIELDS)) from one rank's per-QP outputs (NumPy arrays)."""
     status = np.asarray(status)
     stats = np.asarray(stats)
@@ -44,6 +44,8 @@ def local_stats(status, iters, stats, elapsed_ms, flops=0.0):
         rec[13] = stats[:, 0].max()
         rec[14] = stats[:, 1].max()
     rec[15] = flops
+    rec[16] = (path == 4).sum()          # finished by the Riccati pre-pass (no active constraint)
+    rec[17] = flops_route
     return rec
 
 

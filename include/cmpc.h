@@ -51,7 +51,7 @@ typedef struct cmpc_handle cmpc_handle;
 #define CMPC_STAT_NACT    4   /* active inequality rows at the solution       */
 #define CMPC_STAT_RHO     5   /* final ADMM rho                               */
 #define CMPC_STAT_ASITERS 6   /* active-set iterations                        */
-#define CMPC_STAT_PATH    7   /* 0 unconstrained, 1 active-set, 2 ADMM, 3 ADMM+polish */
+#define CMPC_STAT_PATH    7   /* 0 unconstrained, 1 active-set, 2 ADMM, 3 ADMM+polish, 4 unconstrained via the Riccati pre-pass */
 
 /* Replaces CentroidalMPC.__init__ (centroidal_mpc.py:41-67): allocates nothing on the device but
  * fixes the horizon N (16, 32 or 48 ...; <= 48) and the largest batch the handle will see.     */
@@ -75,11 +75,14 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax);
  * two implementations can be compared on the same inputs.                                        */
 int cmpc_set_generic(cmpc_handle* h, int on);
 
-/* Nominal pre-pass (opt-in, default off; active-set mode with raw inputs): a Riccati sweep, one warp per
- * robot, finishes every robot whose unconstrained minimiser already satisfies the friction-pyramid and
- * fz_min rows (nominal trot) and hands the others to the condensed active-set
- * kernel through a device work-list.  Results are the same optimum either way; round-1 measurements
- *  have the first version of the sweep slower than the path it replaces, hence off. */
+/* Nominal pre-pass (active-set mode with raw inputs): a Riccati sweep finishes every robot whose unconstrained
+ * minimiser already satisfies the friction-pyramid and fz_min rows (nominal trot) and hands
+ * the others to the condensed active-set kernel through a device work-list.  Same optimum either way.
+ *   0  off: every robot through the condensed kernel
+ *   1  reference sweep, one robot per warp (cmpc_riccati.cuh; the version the host emulation tests)
+ *   2  register-resident sweep, two robots per warp (cmpc_riccati2.cuh)
+ *   3  (default) = 2 with the sixteen robots of a CTA in lock-step, so that they share fetched instruction lines;
+ *      falls back to 2 when sixteen robots do not fit shared memory (N > 16)                              */
 int cmpc_set_prepass(cmpc_handle* h, int on);
 
 /* ComTraj.generate_traj (com_trajectory.py:27-211 with gait.py:21-24,40-74), batched: reference trajectory,

@@ -48,7 +48,7 @@ nxt = None
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 solved = 0
 worst_rp = worst_rd = 0.0
-paths = np.zeros(4)
+paths = np.zeros(5)
 WARM = 10
 nchecks = 0
 for c in range(C + WARM):
@@ -61,7 +61,7 @@ for c in range(C + WARM):
     if c >= WARM and (c % 50 == 0 or c == C + WARM - 1):
         st = sol["stats"].cpu().numpy(); nchecks += 1
         solved += int((sol["status"].cpu().numpy() == 1).sum()); worst_rp = max(worst_rp, st[:, 0].max()); worst_rd = max(worst_rd, st[:, 1].max())
-        paths += np.bincount(st[:, 7].astype(int), minlength=4)[:4]
+        paths += np.bincount(st[:, 7].astype(int), minlength=5)[:5]
 ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1])
 xf = state.x.cpu().numpy()

@@ -28,7 +28,7 @@ for N in (16, 32, 48):
         errs.append(force_error(u[b], o["sol"]["U"]))
     t = float(np.median(ts))
     row = {"horizon": N, "condensed_vars": 12 * N, "batch": B, "max_stance": ms, "kernel_ms_p50": t, "qps": B / t * 1e3,
-           "solved_frac": float((st == 1).mean()), "paths": np.bincount(stats[:, 7].astype(int), minlength=4).tolist(),
+           "solved_frac": float((st == 1).mean()), "paths": np.bincount(stats[:, 7].astype(int), minlength=5).tolist(),
            "n_free_mean": float(stats[:, 3].mean()), "r_prim_max": float(stats[:, 0].max()), "r_dual_max": float(stats[:, 1].max()),
            "force_err_abs_max_N": float(max(e[0] for e in errs)), "force_err_vs_tolerance_max": float(max(e[1] for e in errs)),
            "oracle_samples": len(errs),

@@ -34,7 +34,7 @@ def main():
                     mpc.solve_QP(None, traj)
                     ts.append(mpc.solve_time)
                 st = mpc.last_stats.cpu().numpy()
-                path = np.bincount(st[:, 7].astype(int), minlength=4).tolist()
+                path = np.bincount(st[:, 7].astype(int), minlength=5).tolist()
                 t = float(np.median(ts))
                 print(json.dumps({"B": B, "stress": stress, "max_stance": ms, "ms": round(t, 3),
                                   "qps": round(B / t * 1e3, 1), "paths": path,
