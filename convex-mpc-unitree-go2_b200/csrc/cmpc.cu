@@ -427,6 +427,7 @@ struct cmpc_handle {
     int prepass = 3;       // Riccati pre-pass ahead of the condensed kernel (active-set mode, raw inputs): 0 off, 1 v1, 2 v2, 3 v2 lock-step
     // pre-pass slots (work-list, its counter, gain scratch); calls rotate over them so that solves enqueued on
     // different streams do not share one
+    int prepass_min_batch = 2048;   // CMPC_PREPASS_MIN_BATCH overrides (diagnostics)
     struct PreSlot { int* worklist = nullptr; int* count = nullptr; double* gains = nullptr; int cap = 0; size_t gain_doubles = 0; };
     PreSlot pre[4];
     unsigned pre_next = 0;
@@ -562,6 +563,7 @@ int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
     h->smem_optin = (size_t)v;
     CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     h->smem_per_sm = (size_t)v;
+    if (const char* e = getenv("CMPC_PREPASS_MIN_BATCH")) { const int mb = atoi(e); if (mb >= 1) h->prepass_min_batch = mb; }
     *out = h;
     return 0;
 }
@@ -741,7 +743,9 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         if (plan_launch_fast(h, h->nfmax, B, &smem, &hp, &stride, &grid_f)) return -1;
         const int* wl = nullptr;
         const int* wlc = nullptr;
-        if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET) {
+        // small batches are latency-bound (fewer robots than CTA slots x a few rounds): the extra kernel in front only
+        // adds to the latency there (batch 1: 45 -> 99 us), so the pre-pass starts at prepass_min_batch robots
+        if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET && B >= h->prepass_min_batch) {
             // Riccati pre-pass: finishes the robots without an active constraint, lists the others
             ric::WsR wr;
             const size_t per_warp = (ric::ws_carve_ric(wr, reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20)), h->N) + 15) & ~(size_t)15;

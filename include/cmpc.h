@@ -82,7 +82,8 @@ int cmpc_set_generic(cmpc_handle* h, int on);
  *   1  reference sweep, one robot per warp (cmpc_riccati.cuh; the version the host emulation tests)
  *   2  register-resident sweep, two robots per warp (cmpc_riccati2.cuh)
  *   3  (default) = 2 with the sixteen robots of a CTA in lock-step, so that they share fetched instruction lines;
- *      falls back to 2 when sixteen robots do not fit shared memory (N > 16)                              */
+ *      falls back to 2 when sixteen robots do not fit shared memory (N > 16)
+ * Batches below 2 048 robots skip the pre-pass (they are latency-bound; the extra launch only adds latency).  */
 int cmpc_set_prepass(cmpc_handle* h, int on);
 
 /* ComTraj.generate_traj (com_trajectory.py:27-211 with gait.py:21-24,40-74), batched: reference trajectory,

@@ -16,10 +16,14 @@ fi
 python tools/prof_case.py 4736 0.0 40 > $O/${TAG}_prof_plain.log 2>&1; rc=$?; echo "prof_case rc=$rc"
 if [ $rc -eq 0 ]; then
   cp convex-mpc-unitree-go2_b200/libcmpc.so $O/${TAG}_prof.so
-  ncu --set full --clock-control none --import-source on -k regex:solve_fast_kernel -s 2 -c 1 -f -o $O/${TAG}_prof \
+  # the two kernels of one cmpc_solve call (Riccati pre-pass, condensed kernel on the work-list), third solve of the run
+  ncu --set full --clock-control none --import-source on -k "regex:riccati2_lockstep_kernel|solve_fast_kernel" -s 4 -c 2 -f -o $O/${TAG}_prof \
       python tools/prof_case.py 4736 0.0 40 > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-  # DRAM traffic of one launch at the bench's own size (65 536 robots)
+  # DRAM traffic and durations of the same two kernels at the bench's own size (65 536 robots)
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-      -k regex:solve_fast_kernel -s 2 -c 1 --csv --log-file $O/${TAG}_traffic_65536.csv \
+      -k "regex:riccati2_lockstep_kernel|solve_fast_kernel" -s 4 -c 2 --csv --log-file $O/${TAG}_traffic_65536.csv \
       python tools/prof_case.py 65536 0.0 40 > $O/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
 fi
+python tools/closed_loop.py 1024 500 $O/${TAG}_closed_loop.json > /dev/null 2>&1; echo "closed loop rc=$?"
+python bench.py --sweep > $O/${TAG}_sweep.log 2>&1; cp $O/sweep_active_set.json $O/${TAG}_sweep_active_set.json; echo "sweep rc=$?"
+python tools/horizon_sweep.py 16384 > $O/${TAG}_horizon.log 2>&1; cp $O/horizon_sweep.json $O/${TAG}_horizon_sweep.json; echo "horizon rc=$?"

@@ -55,6 +55,11 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kernel}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if starts:      # several kernels in the report: keep the first block of the one asked for
+        b0 = next((i for i in starts if kernel in rows[i][1]), starts[0])
+        b1 = next((i for i in starts if i > b0), len(rows))
+        rows = rows[b0:b1]
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")

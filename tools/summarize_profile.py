@@ -28,7 +28,9 @@ with open(os.path.join(out, f"{tag}_launches_summary.csv"), "w") as f:
 # ---- raw metrics of the profiled kernel
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
-names, units, vals = rr[0], rr[1], rr[2]
+names, units = rr[0], rr[1]
+ki = names.index("Kernel Name")
+vals = next((r for r in rr[2:] if kernel in r[ki]), rr[2])      # the report may hold several kernels
 want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -44,6 +46,13 @@ for k in want:
 # ---- stall reasons (whole kernel) from the source page
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kernel}"], capture_output=True, text=True).stdout
 sr = list(csv.reader(io.StringIO(src)))
+# a report with several kernels prints one block per kernel ("Kernel Name" row, header row, instructions): keep the
+# first block of the kernel asked for
+starts = [i for i, r in enumerate(sr) if r and r[0] == "Kernel Name"]
+if starts:
+    b0 = next((i for i in starts if kernel in sr[i][1]), starts[0])
+    b1 = next((i for i in starts if i > b0), len(sr))
+    sr = sr[b0:b1]
 h = next(i for i, r in enumerate(sr) if r and r[0] == "Address")
 sh = sr[h]
 cols = [i for i, n in enumerate(sh) if n.startswith("stall_") and "Not Issued" not in n]
