@@ -314,7 +314,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "CentroidalMPC.solve_host -> cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64_fma", "kernel": "solve_fast_kernel", "achieved": ach_tf, "peak": f64.value,
+            "roofline": {"bound": "fp64_fma", "kernel": "riccati2_lockstep_kernel + solve_fast_kernel (one cmpc_solve call)" if args.prepass else "solve_fast_kernel", "achieved": ach_tf, "peak": f64.value,
                          "unit": "TFLOP/s", "frac": ach_tf / f64.value, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_ms": kms, "algorithmic_flops_per_launch": flops,
                          "frac_route_actual": flops_route / (kms * 1e-3) / 1e12 / f64.value,

@@ -783,12 +783,14 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 const size_t smem_2 = per_half * hpb;
                 int per_sm2 = (int)(h->smem_per_sm / (smem_2 + 1024));
                 if (per_sm2 > 8) per_sm2 = 8;
-                const size_t smem_ls = per_half * (kRic2LsThreads / 32) * 2;
-                if (h->prepass == 3 && smem_ls <= h->smem_optin) {
-                    const int hpl = (kRic2LsThreads / 32) * 2;
+                // lock-step CTA: as many robots as fit shared memory (pairs: two per warp), at most sixteen
+                int hpl = (int)(h->smem_optin / per_half) & ~1;
+                if (hpl > (kRic2LsThreads / 32) * 2) hpl = (kRic2LsThreads / 32) * 2;
+                const size_t smem_ls = per_half * (size_t)hpl;
+                if (h->prepass == 3 && hpl >= 4) {
                     const int want3 = (B + hpl - 1) / hpl;
                     CU_TRY(cudaFuncSetAttribute((const void*)riccati2_lockstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ls));
-                    riccati2_lockstep_kernel<<<want3 < h->sm_count ? want3 : h->sm_count, kRic2LsThreads, smem_ls, (cudaStream_t)stream>>>(
+                    riccati2_lockstep_kernel<<<want3 < h->sm_count ? want3 : h->sm_count, 16 * hpl, smem_ls, (cudaStream_t)stream>>>(
                         h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd, ps.worklist, ps.count, per_half);
                 } else if (h->prepass >= 2 && per_sm2 >= 1 && gd * (size_t)h->sm_count * per_sm2 * hpb <= ps.gain_doubles) {
                     const int want2 = (B + hpb - 1) / hpb, cap2 = h->sm_count * per_sm2;
