@@ -39,7 +39,7 @@ for leg in range(4):
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 state = ct.RobotState(t(x), t(np.swapaxes(R, 1, 2).copy()), t(lever), t(np.full(B, records.GO2_MASS)),
                       t(np.einsum("bij,j,bkj->bik", R, records.GO2_I_BODY, R)))
-cmd = [t(rng.uniform(-0.8, 0.8, B)), t(rng.uniform(-0.4, 0.4, B)), t(np.full(B, 0.27)), t(rng.uniform(-2.0, 2.0, B))]
+cmd = [t(rng.uniform(-0.8, 0.8, B)), t(rng.uniform(-0.4, 0.4, B)), t(np.full(B, 0.27)), t(rng.uniform(-4.0, 4.0, B))]   # BASELINE configs[1]: forward, lateral 0.4 m/s, yaw 4 rad/s
 
 traj = ct.ComTraj(state, hip_offset=hip, device=dev)
 traj.generate_traj(state, gait, 0.0, *cmd, dt)
