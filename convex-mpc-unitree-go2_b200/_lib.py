@@ -30,6 +30,8 @@ PROTOTYPES = {
     "cmpc_generate_traj": (c_int, [c_int, c_int, c_int] + [c_void_p] * 5 + [c_double, c_double, c_double, c_dp, c_dp] +
                            [c_void_p] * 4 + [c_void_p]),
     "cmpc_srb_step": (c_int, [c_int, c_int, c_int] + [c_void_p] * 6 + [c_double, c_dp, c_dp] + [c_void_p] * 4 + [c_void_p]),
+    "cmpc_stance_torque": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_dp, c_double,
+                           c_void_p, c_void_p, c_void_p]),
     "cmpc_pack_contact": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "cmpc_dynamics": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                               c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -151,3 +151,23 @@ def srb_step(state, traj, u, mpc_period, I_body, stance_offset, out=None, stream
                                      out.x.data_ptr(), out.R_world_to_body.data_ptr(), out.inertia.data_ptr(),
                                      out.foot_lever_world.data_ptr(), ctypes.c_void_p(s)))
     return out
+
+
+def stance_torque(J_foot_world, u, time_now, gait, N, tau_max=45.0, phase_offset=PHASE_OFFSET, stream=None):
+    """tau = clip(J^T (-f), +-tau_max) for the legs in stance at ``time_now``, zero for swing legs -- the stance
+    branch of ``LegController.compute_leg_torque`` (leg_controller.py:100-101) plus the motor saturation of
+    test_MPC.py:227, batched (``cmpc_stance_torque``).  ``J_foot_world`` (B,4,3,3), ``u`` the solver's (B,12N) force
+    buffer, ``time_now`` (B,) device tensors.  Returns (tau (B,12), mask_now (B,4) int32)."""
+    lib = _lib.load()
+    dev = u.device
+    B = u.shape[0]
+    J = _dev(J_foot_world, dev, (B, 4, 3, 3))
+    t0 = _dev(time_now, dev, (B,))
+    tau = torch.empty(B, 12, dtype=torch.float64, device=dev)
+    mask = torch.empty(B, 4, dtype=torch.int32, device=dev)
+    s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.cmpc_stance_torque(dev.index or 0, int(N), B, J.data_ptr(), u.reshape(B, 12 * N).data_ptr(), t0.data_ptr(),
+                                          float(gait.gait_hz), float(gait.gait_duty), _lib.darr(phase_offset), float(tau_max),
+                                          tau.data_ptr(), mask.data_ptr(), ctypes.c_void_p(s)))
+    return tau, mask

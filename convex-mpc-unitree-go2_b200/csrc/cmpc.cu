@@ -322,6 +322,20 @@ __global__ void srb_step_kernel(int B, int N, const double* __restrict__ x, cons
                        lever_out + (size_t)b * 12);
 }
 
+// Stance torque mapping (cmpc_traj.cuh): one thread per (robot, leg).
+__global__ void stance_torque_kernel(int B, int N, const double* __restrict__ J, const double* __restrict__ u,
+                                     const double* __restrict__ t_now, double period, double duty, double o0, double o1,
+                                     double o2, double o3, double tau_max, double* __restrict__ tau, int32_t* __restrict__ mask_now) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * B) return;
+    const int b = e >> 2, leg = e & 3;
+    const double off = leg == 0 ? o0 : (leg == 1 ? o1 : (leg == 2 ? o2 : o3));
+    const int st = traj::stance_bit_now(t_now[b], 0.0, 0, period, off, duty);
+    traj::stance_torque_leg(J + ((size_t)b * 4 + leg) * 9, u + (size_t)b * 12 * N + 3 * leg, st, tau_max,
+                            tau + (size_t)b * 12 + 3 * leg);
+    if (mask_now) mask_now[e] = st;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Roofline denominators: dependent-free DFMA streams and shared-memory 8-byte reads.
 // ---------------------------------------------------------------------------------------------
@@ -670,6 +684,24 @@ int cmpc_srb_step(int device, int N, int B, const double* x, const double* u, co
     srb_step_kernel<<<(B + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
         B, N, x, u, x_ref, r_foot, I_world, mass, T, I_body[0], I_body[1], I_body[2], s[0], s[1], s[2], s[3], s[4], s[5], s[6],
         s[7], s[8], s[9], s[10], s[11], x_out, R_world_to_body_out, I_world_out, foot_lever_out);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_stance_torque(int device, int N, int B, const double* J_foot_world, const double* u, const double* time_now,
+                       double gait_hz, double duty, const double phase_offset[4], double tau_max, double* tau,
+                       int32_t* mask_now, void* stream) {
+    if (!J_foot_world || !u || !time_now || !phase_offset || !tau) return fail("null argument");
+    if (N < 1 || N > 48) return fail("horizon N must be in [1, 48]");
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(device));
+    const double period = 1 / gait_hz;   // gait.py:17
+    const int tpb = 128, total = 4 * B;
+    stance_torque_kernel<<<(total + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
+        B, N, J_foot_world, u, time_now, period, duty, phase_offset[0], phase_offset[1], phase_offset[2], phase_offset[3],
+        tau_max, tau, mask_now);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -156,5 +156,24 @@ CMPC_HD void srb_step_one(int N, const double* x, const double* u0, const double
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Stance torque mapping: the step after the path.  For a leg in stance at time_now
+// (gait.compute_current_mask, gait.py:21-24)  tau = J^T (-f)  with J the 3x3 world-aligned translational foot
+// Jacobian over the leg's three joints (leg_controller.py:100-101, go2_robot_data.py:286-300) and f the
+// first-step contact force of the MPC (test_MPC.py:196), then the motor saturation  clip(tau, -tau_max, tau_max)
+// (test_MPC.py:227).  Swing legs get zero here: their torque comes from the swing-leg controller
+// (leg_controller.py:66-98: operational-space PD with the joint-space inertia), which is not on this path.
+// ----------------------------------------------------------------------------------------------
+CMPC_HD void stance_torque_leg(const double* J, const double* f, int stance, double tau_max, double* tau) {
+    for (int j = 0; j < 3; ++j) {
+        double t = 0.0;
+        if (stance) {
+            t = -(J[0 * 3 + j] * f[0] + J[1 * 3 + j] * f[1] + J[2 * 3 + j] * f[2]);
+            t = fmin(fmax(t, -tau_max), tau_max);
+        }
+        tau[j] = t;
+    }
+}
+
 }  // namespace traj
 }  // namespace cmpc

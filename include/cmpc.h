@@ -113,6 +113,17 @@ int cmpc_srb_step(int device, int N, int B, const double* x, const double* u, co
                   const double stance_offset[12], double* x_out, double* R_world_to_body_out, double* I_world_out,
                   double* foot_lever_out, void* stream);
 
+/* Stance torque mapping, the step after the path: for every leg in stance at time_now
+ * (Gait.compute_current_mask, gait.py:21-24, bit-exact)  tau = clip(J^T (-f), -tau_max, tau_max)  with f the
+ * first-step force of the MPC (leg_controller.py:100-101, test_MPC.py:196,227); swing legs get 0 (their torque is
+ * the swing-leg controller's, leg_controller.py:66-98, not on this path).  Device arrays:
+ *   J_foot_world (B,4,3,3) row-major world-aligned translational foot Jacobians over the leg's three joints
+ *   (go2_robot_data.py:286-300);  u (B,12N) as cmpc_solve wrote it;  time_now (B);  tau (B,12) out;
+ *   mask_now (B,4) int32 out, may be NULL.                                                               */
+int cmpc_stance_torque(int device, int N, int B, const double* J_foot_world, const double* u, const double* time_now,
+                       double gait_hz, double duty, const double phase_offset[4], double tau_max, double* tau,
+                       int32_t* mask_now, void* stream);
+
 /* Gait.compute_contact_table (gait.py:26-37), bit-exact.  t0 (B) device; mask_out (B, W) device. */
 int cmpc_contact_table(cmpc_handle* h, int B, const double* t0, double dt, double gait_hz,
                        double duty, const double phase_offset[4], uint64_t* mask_out, void* stream);

@@ -314,6 +314,27 @@ def test_enqueue_and_cuda_graph_replay_equal_solve_QP(mod):
     assert np.abs(c._u.view(512, 16, 12).transpose(1, 2).cpu().numpy() - ref)[exact].max() < 1e-7
 
 
+def test_stance_torque_mapping(mod):
+    """cmpc_stance_torque (SURVEY.md 8 f3) against leg_controller.py:100-101 + test_MPC.py:227 restated in NumPy;
+    the current-time gait mask against the reference-pinned oracle (gait.py:21-24)."""
+    from convex_mpc_b200 import com_trajectory as ct
+    from oracle import traj_ref
+    rng = np.random.default_rng(12)
+    B, N = 4096, 16
+    J = rng.normal(0, 0.2, (B, 4, 3, 3))
+    u = rng.normal(0, 60, (B, 12 * N)); u[:, 2:12:3] = np.abs(u[:, 2:12:3]) + 30
+    t_now = np.concatenate([1e-3 * rng.integers(0, 100000, B // 2), rng.uniform(0, 50, B - B // 2)])
+    gait = ct.Gait(3.0, 0.6)
+    tau, mask = ct.stance_torque(dev(J), dev(u), dev(t_now), gait, N, tau_max=45.0)
+    tau, mask = tau.cpu().numpy(), mask.cpu().numpy()
+    ref_mask = np.stack([traj_ref.current_mask(t, 3.0, 0.6) for t in t_now])
+    assert np.array_equal(mask, ref_mask)
+    f = u[:, :12].reshape(B, 4, 3)
+    ref = np.clip(np.einsum("blij,bli->blj", J, -f), -45.0, 45.0) * ref_mask[:, :, None]     # J^T (-f), clipped
+    assert np.abs(tau.reshape(B, 4, 3) - ref).max() < 1e-12
+    assert (np.abs(tau) == 45.0).any() and (tau.reshape(B, 4, 3)[ref_mask == 0] == 0).all()
+
+
 def test_drop_in_single_robot_api(mod):
     """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
     rec = records.random_records(1, seed=9, stress=1.0)
