@@ -889,9 +889,19 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
     // chunks sized so that copies of one chunk hide behind the solve of the other
     int chunk = B <= 4096 ? B : (B < 32768 ? 8192 : 16384);   // measured at 65 536 robots: 4096 -> 12.3 ms, 8192 -> 11.6, 16384 -> 11.3, 32768 -> 11.9
     if (const char* e = getenv("CMPC_HOST_CHUNK")) { const int v = atoi(e); if (v >= 256) chunk = v < B ? v : B; }   // tuning
-    int ci = 0;
-    for (int lo = 0; lo < B; lo += chunk, ++ci) {
-        const int nb = (B - lo) < chunk ? (B - lo) : chunk;
+    // the first copy in and the last copy out cannot hide behind anything: ramp the chunk size up from 4 096
+    // (4096, 8192, then `chunk`) and finish with a 4 096-robot chunk, so that only small transfers are exposed
+    const bool ramp = (B >= 4 * chunk) && !getenv("CMPC_HOST_CHUNK");
+    int ci = 0, nb = 0;
+    for (int lo = 0; lo < B; lo += nb, ++ci) {
+        int want = chunk;
+        if (ramp) {
+            if (ci == 0) want = 4096;
+            else if (ci == 1) want = 8192;
+            const int rem = B - lo;
+            if (rem > 4096 && rem - want < 4096) want = rem - 4096;      // leave a small last chunk
+        }
+        nb = (B - lo) < want ? (B - lo) : want;
         cudaStream_t s = q.s[ci & 1];
         const size_t o = (size_t)lo;
         CU_TRY(cudaMemcpyAsync(q.x0 + o * 12, x0 + o * 12, (size_t)nb * 12 * sizeof(double), cudaMemcpyHostToDevice, s));
