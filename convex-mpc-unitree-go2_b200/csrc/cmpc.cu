@@ -194,12 +194,29 @@ solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm,
     const int N = bi.N;
     // with a work-list (robots the Riccati pre-pass could not finish) the loop runs over its entries
     const int count = worklist ? *wl_count : B;
-    for (int it = blockIdx.x; it < count; it += gridDim.x) {
-        const int b = worklist ? worklist[it] : it;
-        QpIn in = qp_in(bi, b);
-        QpOut o = qp_out(bo, b, N);
-        fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
-        __syncthreads();
+    if (worklist) {
+        // work-list entries differ a lot in cost (active-set iterations): CTAs take the next entry from a cursor
+        // (wl_count[1], zeroed with the counter) instead of a fixed stride
+        __shared__ int next_it;
+        for (;;) {
+            if (threadIdx.x == 0) next_it = atomicAdd(const_cast<int*>(wl_count) + 1, 1);
+            __syncthreads();
+            const int it = next_it;
+            __syncthreads();
+            if (it >= count) break;
+            const int b = worklist[it];
+            QpIn in = qp_in(bi, b);
+            QpOut o = qp_out(bo, b, N);
+            fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
+            __syncthreads();
+        }
+    } else {
+        for (int it = blockIdx.x; it < count; it += gridDim.x) {
+            QpIn in = qp_in(bi, it);
+            QpOut o = qp_out(bo, it, N);
+            fast::solve_one_fast(c, p, in, o, w, nfmax, warm);
+            __syncthreads();
+        }
     }
     PHASE_KERNEL_END();
 }
@@ -800,7 +817,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                         CU_TRY(cudaMalloc(&q.worklist, (size_t)B * sizeof(int)));
                         q.cap = B;
                     }
-                    if (!q.count) CU_TRY(cudaMalloc(&q.count, sizeof(int)));
+                    if (!q.count) CU_TRY(cudaMalloc(&q.count, 2 * sizeof(int)));      // [0] work-list length, [1] cursor of the condensed kernel
                     if (q.gain_doubles < need_g) {
                         if (q.gains) cudaFree(q.gains);
                         q.gains = nullptr;
@@ -809,7 +826,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                     }
                 }
                 auto& ps = h->pre[h->pre_next++ & 3u];
-                CU_TRY(cudaMemsetAsync(ps.count, 0, sizeof(int), (cudaStream_t)stream));
+                CU_TRY(cudaMemsetAsync(ps.count, 0, 2 * sizeof(int), (cudaStream_t)stream));
                 const size_t per_half = ric2::half_bytes(h->N);
                 const int hpb = (kRic2Threads / 32) * 2;
                 const size_t smem_2 = per_half * hpb;
