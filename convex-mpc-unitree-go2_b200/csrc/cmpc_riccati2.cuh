@@ -218,7 +218,7 @@ __device__ __forceinline__ void back_stage(unsigned hmask, int hl, int i, bool a
                         if (!(piv > 0.0)) pmin = -1.0;
                         const double dj = rsqrt_fast(piv);
                         const double l = Ga[j] * dj;
-                        if (j + 1 < 12) piv = shfl16(hmask, Ga[j + 1 < 12 ? j + 1 : 11] - l * l, j + 1 < 12 ? j + 1 : 11);
+                        if (j + 1 < 12) piv = shfl16(hmask, Ga[(j + 1) % 12] - l * l, (j + 1) % 12);   // next pivot goes out first
                         const double wj = (j == hl) ? dj : -dj * sw[j];
                         Wc[j] = wj;
 #pragma unroll
