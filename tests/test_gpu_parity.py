@@ -285,6 +285,29 @@ def test_device_resident_closed_loop(mod):
     assert 0.2 < state.x[:, 2].mean().item() < 0.35           # still walking, not fallen through the floor
 
 
+@pytest.mark.parametrize("N", [32, 48])
+def test_riccati_prepass_longer_horizons(mod, N):
+    """The lock-step pre-pass with fewer robots per CTA (20 KB / 28 KB of shared memory per robot at N = 32 / 48)
+    against the condensed kernel alone and the oracle."""
+    B = 2048
+    rec = records.random_records(B, N=N, seed=700 + N, stress=0.2)
+    ms = 4 * (int(np.floor(rec.duty * N)) + 1)
+    a, traj = make_mpc(mod, rec, max_stance=ms)                  # default: pre-pass on from 2 048 robots
+    b, _ = make_mpc(mod, rec, max_stance=ms, prepass=0)
+    sa, sb = a.solve_QP(None, traj), b.solve_QP(None, traj)
+    sta, stb = sa["stats"].cpu().numpy(), sb["stats"].cpu().numpy()
+    assert (sa["status"].cpu().numpy() == 1).all() and (sb["status"].cpu().numpy() == 1).all()
+    assert np.array_equal(np.where(sta[:, 7] == 4, 0, sta[:, 7]), stb[:, 7])
+    assert (sta[:, 7] == 4).mean() > 0.2
+    exact = ~np.isin(stb[:, 7], (2, 3))
+    ua, ub = sa["u"].cpu().numpy(), sb["u"].cpu().numpy()
+    assert np.abs(ua - ub)[exact].max() < 1e-6
+    assert np.abs(sa["lam_a"].full() - sb["lam_a"].full())[exact].max() < 1e-5
+    for bi in (0, 777):
+        o = oracle_solution(rec, bi)
+        assert force_error(ua[bi].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+
+
 def test_enqueue_and_cuda_graph_replay_equal_solve_QP(mod):
     """CentroidalMPC.enqueue (no host synchronisation) gives solve_QP's results, eagerly and replayed from a CUDA
     graph (the capture path tools/closed_loop.py uses)."""
