@@ -308,6 +308,46 @@ def test_riccati_prepass_longer_horizons(mod, N):
         assert force_error(ua[bi].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
 
 
+@pytest.mark.parametrize("version", [1, 2, 3])
+def test_riccati_prepass_irregular_contact_schedules(mod, version):
+    """Contact tables the trot never produces -- a flight phase (no leg in stance for two steps), single-leg and
+    three-leg stance steps, all four legs -- drive the pre-pass through its run-time-m stage code (m = 0, 3, 9, 12)
+    and the all-stance case; results against the condensed kernel alone and the oracle."""
+    B, N = 2048, 16
+    rec = records.random_records(B, seed=313, stress=0.0)
+    rng = np.random.default_rng(7)
+    ct = np.ones((B, 4, N), dtype=np.int32)
+    ct[: B // 2] = (rng.random((B // 2, 4, N)) < 0.7).astype(np.int32)      # arbitrary patterns: 0..4 legs per step
+    ct[: B // 2, :, 5:7] = 0                                                 # flight phase
+    ct[: B // 2, 1:, 9] = 0; ct[: B // 2, 0, 9] = 1                          # one leg only
+    rf = rec.r_foot.copy()
+    hips = np.array([[0.1934, 0.142], [0.1934, -0.142], [-0.1934, 0.142], [-0.1934, -0.142]])
+    for leg in range(4):                                                     # lever arms wherever the table says stance
+        rf[:, leg, 0, :] = hips[leg, 0]; rf[:, leg, 1, :] = hips[leg, 1]; rf[:, leg, 2, :] = -0.27
+    rec = records.Records(rec.x0, rec.x_ref, rf * ct[:, :, None, :], rec.I_world, rec.mass, rec.t0, rec.dt, rec.gait_hz, rec.duty, N)
+    sols = []
+    for pp in (version, 0):
+        traj = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+        traj.contact_table = dev(ct)
+        mpc = mod.CentroidalMPC(None, traj, verbose=False, prepass=pp)
+        sols.append(mpc.solve_QP(None, traj))
+    sa, sb = sols
+    sta, stb = sa["stats"].cpu().numpy(), sb["stats"].cpu().numpy()
+    assert np.array_equal(sa["status"].cpu().numpy(), sb["status"].cpu().numpy())
+    ok = (sb["status"].cpu().numpy() == 1) & ~np.isin(stb[:, 7], (2, 3))
+    assert ok.mean() > 0.8
+    assert np.array_equal(np.where(sta[:, 7] == 4, 0, sta[:, 7])[ok], stb[ok, 7])
+    assert (sta[: B // 2, 7] == 4).sum() > 20 and (sta[B // 2:, 7] == 4).sum() > 20     # both halves reach the pre-pass
+    ua, ub = sa["u"].cpu().numpy(), sb["u"].cpu().numpy()
+    assert np.abs(ua - ub)[ok].max() < 1e-6
+    assert np.abs(sa["x"].full() - sb["x"].full())[ok].max() < 1e-6
+    assert np.abs(sa["lam_a"].full() - sb["lam_a"].full())[ok].max() < 1e-5
+    done = np.flatnonzero(ok & (sta[:, 7] == 4))
+    for bi in (done[0], done[len(done) // 2], done[-1]):
+        o = oracle_solution(rec, bi, contact=ct[bi])
+        assert force_error(ua[bi].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+
+
 def test_enqueue_and_cuda_graph_replay_equal_solve_QP(mod):
     """CentroidalMPC.enqueue (no host synchronisation) gives solve_QP's results, eagerly and replayed from a CUDA
     graph (the capture path tools/closed_loop.py uses)."""
