@@ -183,11 +183,12 @@ solve_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, doub
 template <bool kExternal>
 __global__ void __launch_bounds__(kThreads, 2)
 solve_fast_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, double* hb_scratch, size_t hb_stride,
-                  const int* __restrict__ worklist, const int* __restrict__ wl_count) {
+                  const int* __restrict__ worklist, const int* __restrict__ wl_count, double* yg_scratch, size_t yg_stride) {
     extern __shared__ __align__(16) unsigned char smem[];
     fast::WsF w;
     if (kExternal) fast::ws_carve_fast<2>(w, smem, bi.N, nfmax, hb_scratch + (size_t)blockIdx.x * hb_stride);
     else fast::ws_carve_fast<1>(w, smem, bi.N, nfmax, nullptr);
+    if (yg_scratch) w.Yg = yg_scratch + (size_t)blockIdx.x * yg_stride;      // rows of large working sets (L2-resident)
     const fast::Cx c = fast::make_cx(threadIdx.x, blockDim.x);
     fast::init_tables(c, w);
     PHASE_KERNEL_BEGIN();
@@ -462,6 +463,9 @@ struct cmpc_handle {
     struct PreSlot { int* worklist = nullptr; int* count = nullptr; double* gains = nullptr; int cap = 0; size_t gain_doubles = 0; };
     PreSlot pre[4];
     unsigned pre_next = 0;
+    double* yg_scratch = nullptr;   // per-CTA rows of large working sets (kcap x npad doubles each)
+    size_t yg_stride = 0;
+    int yg_ctas = 0;
     double* hp_scratch = nullptr;   // packed-matrix scratch when it does not fit shared memory
     size_t hp_stride = 0;
     int hp_ctas = 0;
@@ -603,6 +607,7 @@ int cmpc_destroy(cmpc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->hp_scratch) cudaFree(h->hp_scratch);
+    if (h->yg_scratch) cudaFree(h->yg_scratch);
     for (auto& ps : h->pre) { if (ps.worklist) cudaFree(ps.worklist); if (ps.count) cudaFree(ps.count); if (ps.gains) cudaFree(ps.gains); }
     auto& q = h->hp;
     void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters};
@@ -858,8 +863,21 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 grid_f = B < cap_f ? B : cap_f;
             }
         }
-        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc);
-        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc);
+        {   // global scratch for the rows of working sets that do not fit shared memory (allocated once)
+            const size_t npad = ((3 * (size_t)h->nfmax + 7) / 8) * 8;
+            const size_t st = (size_t)fast::kcap_fast(h->nfmax) * npad;
+            const int ctas = h->sm_count * 2;
+            if (h->yg_stride < st || h->yg_ctas < ctas) {
+                if (h->yg_scratch) cudaFree(h->yg_scratch);
+                h->yg_scratch = nullptr;
+                CU_TRY(cudaMalloc(&h->yg_scratch, st * ctas * sizeof(double)));
+                h->yg_stride = st; h->yg_ctas = ctas;
+            }
+        }
+        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc,
+                                                                                          h->yg_scratch, h->yg_stride);
+        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc,
+                                                                                           h->yg_scratch, h->yg_stride);
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return 0;
