@@ -599,6 +599,7 @@ int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
     CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     h->smem_per_sm = (size_t)v;
     if (const char* e = getenv("CMPC_PREPASS_MIN_BATCH")) { const int mb = atoi(e); if (mb >= 1) h->prepass_min_batch = mb; }
+    if (const char* e = getenv("CMPC_PDAS_MAX_ITER")) { const int v = atoi(e); if (v >= 1) h->p.pdas_max_iter = v; }   // tuning
     *out = h;
     return 0;
 }
