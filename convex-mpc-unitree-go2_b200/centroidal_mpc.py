@@ -176,6 +176,10 @@ class CentroidalMPC:
         check(self._lib.cmpc_create(self.N, self.max_batch, self.device.index or 0, ctypes.byref(h)))
         self._h = h
         self._push_params()
+        self._auto_stance = None
+        if max_stance is None:
+            max_stance = self._stance_bound(traj)
+            self._auto_stance = max_stance
         if max_stance is not None:
             check(self._lib.cmpc_set_max_stance(self._h, int(max_stance)))
         if generic_kernel:
@@ -215,7 +219,25 @@ class CentroidalMPC:
                                         int(bool(o["polish"])), int(o["check_termination"]),
                                         int(o["adaptive_rho_interval"])))
 
+    def _stance_bound(self, traj):
+        """Tight bound on the stance foot-steps of one robot when the GPU computes the contact table itself
+        (``traj.time_now`` + gait) and the horizon spans exactly one gait period, as the reference sets it up
+        (``N = int(gait_period / dt)``, com_trajectory.py:66): N equally spaced samples on the period circle meet a
+        stance arc of length ``duty`` in at most floor(duty N) + 1 points, per leg.  It sizes the shared-memory
+        workspace (40 instead of 64 foot-steps for the 3 Hz / 0.6 trot at N = 16: two CTAs per SM).  Arbitrary
+        caller-supplied tables keep the general bound 4N."""
+        if getattr(traj, "contact_table", None) is not None or getattr(traj, "time_now", None) is None:
+            return None
+        hz, duty, dt = getattr(traj, "gait_hz", None), getattr(traj, "gait_duty", None), getattr(traj, "dt", None)
+        if not hz or duty is None or not dt:
+            return None
+        period = 1.0 / float(hz)
+        if abs(self.N * float(dt) - period) > 1e-9 * period or not (0.0 < float(duty) < 1.0):
+            return None
+        return min(4 * self.N, 4 * (int(np.floor(float(duty) * self.N + 1e-9)) + 1))
+
     def set_max_stance(self, nfmax):
+        self._auto_stance = None
         check(self._lib.cmpc_set_max_stance(self._h, int(nfmax)))
 
     def reset(self):
@@ -266,6 +288,10 @@ class CentroidalMPC:
     def _gather(self, traj, B, stream):
         """Collect device pointers for one call.  Returns (dict of tensors kept alive, use_AdBd)."""
         N = self.N
+        if self._auto_stance is not None and self._stance_bound(traj) != self._auto_stance:
+            # the gait the automatic bound was derived from no longer holds: back to the general bound 4N
+            self._auto_stance = None
+            check(self._lib.cmpc_set_max_stance(self._h, 4 * N))
         t = {}
         t["x0"] = self._dev(traj.initial_x_vec, (B, 12))
         t["x_ref"] = self._dev(traj.compute_x_ref_vec(), (B, 12, N))

@@ -866,7 +866,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         }
         {   // global scratch for the rows of working sets that do not fit shared memory (allocated once)
             const size_t npad = ((3 * (size_t)h->nfmax + 7) / 8) * 8;
-            const size_t st = (size_t)fast::kcap_fast(h->nfmax) * npad;
+            const size_t st = (size_t)fast::kcap_fast(h->nfmax, h->N) * npad;
             const int ctas = h->sm_count * 2;
             if (h->yg_stride < st || h->yg_ctas < ctas) {
                 if (h->yg_scratch) cudaFree(h->yg_scratch);

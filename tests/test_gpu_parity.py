@@ -610,3 +610,22 @@ def test_full_size_properties(mod):
     for b in range(0, rec.B, 2048):
         o = oracle_solution(rec, b)
         assert force_error(un[b].reshape(-1, order="F"), o["sol"]["U"])[1] < 1e-3
+
+
+def test_automatic_stance_bound(mod):
+    """Without ``max_stance`` the host class derives the periodic-gait bound itself (40 foot-steps at N = 16, 3 Hz / 0.6)
+    and falls back to 4N as soon as a caller-supplied contact table arrives; the solutions do not depend on the bound."""
+    rec = records.random_records(512, seed=77, stress=0.3)
+    auto, traj = make_mpc(mod, rec)
+    assert auto._auto_stance == 40
+    full, _ = make_mpc(mod, rec, max_stance=4 * rec.N)
+    assert full._auto_stance is None
+    a, b = auto.solve_QP(None, traj), full.solve_QP(None, traj)
+    assert (a["status"].cpu().numpy() == 1).all() and (b["status"].cpu().numpy() == 1).all()
+    assert float((a["u"] - b["u"]).abs().max()) < 1e-7
+    # a table with every leg in stance over the whole horizon (64 foot-steps) must not be refused
+    tr2 = mod.BatchedComTraj.from_records(rec, device="cuda:0", with_contact_table=True)
+    tr2.contact_table = torch.ones_like(tr2.contact_table)
+    c = auto.solve_QP(None, tr2)
+    assert auto._auto_stance is None
+    assert (c["status"].cpu().numpy() == 1).all()
