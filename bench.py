@@ -296,10 +296,13 @@ def main():
         # DRAM traffic per launch from the committed ncu capture of the same kernel (per-robot figure x robots)
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_v6_dram_traffic.json")))
+            import glob, re
+            caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_v*_dram_traffic.json")),
+                          key=lambda f: [int(x) for x in re.findall(r"\d+", os.path.basename(f))])
+            tr = json.load(open(caps[-1]))                      # the newest committed capture
             if N == 16 and args.mode == "active_set":
                 traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["robots"] * B
-                traffic_src = "profiles/r01_v6_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled per robot)"
+                traffic_src = f"profiles/{os.path.basename(caps[-1])} (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled per robot)"
         except Exception:
             pass
         line = {
