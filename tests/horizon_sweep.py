@@ -1,10 +1,10 @@
 """BASELINE configs[3]: horizon sweep N = 16/32/48 (192/384/576 condensed variables) at batch 16384:
 QPs/s, status counts and the force error against the oracle's exact optimum on a sample.
-    python tools/horizon_sweep.py [B] > gpurun_out/horizon_sweep.json"""
+    python tests/horizon_sweep.py [B] > gpurun_out/horizon_sweep.json"""
 import json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))   # lives under tests/: it checks a sample against the oracle
 from convex_mpc_b200 import records
 from convex_mpc_b200.centroidal_mpc import BatchedComTraj, CentroidalMPC
 from helpers import force_error, oracle_solution

@@ -26,4 +26,4 @@ if [ $rc -eq 0 ]; then
 fi
 python tools/closed_loop.py 1024 500 $O/${TAG}_closed_loop.json > /dev/null 2>&1; echo "closed loop rc=$?"
 python bench.py --sweep > $O/${TAG}_sweep.log 2>&1; cp $O/sweep_active_set.json $O/${TAG}_sweep_active_set.json; echo "sweep rc=$?"
-python tools/horizon_sweep.py 16384 > $O/${TAG}_horizon.log 2>&1; cp $O/horizon_sweep.json $O/${TAG}_horizon_sweep.json; echo "horizon rc=$?"
+python tests/horizon_sweep.py 16384 > $O/${TAG}_horizon.log 2>&1; cp $O/horizon_sweep.json $O/${TAG}_horizon_sweep.json; echo "horizon rc=$?"
