@@ -182,3 +182,21 @@ def test_srb_step_matches_numpy_twin(emul):
     x2, R2, I2, l2 = records.srb_step_host(rec.x0, u[:, :12], rec.x_ref, rec.r_foot, rec.I_world, rec.mass, 0.02, ib, so)
     for a, b in ((xo, x2), (Rw, R2), (Io, I2), (lv, l2)):
         assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max())
+
+
+def test_tighter_stance_bound_keeps_the_working_set_capacity(emul):
+    """A tighter ``max_stance`` only shrinks the workspace: heavily constrained robots at N = 32 (working sets of up
+    to 78 rows under the general bound 4N) must take the same route and reach the same forces under the periodic-gait
+    bound 4(floor(0.6 N) + 1) = 80 (csrc/cmpc_fast.cuh: kcap_fast)."""
+    rec = records.random_records(8, N=32, seed=902, stress=1.0)
+    a, b = emul.solve_fast(rec, nfmax=4 * rec.N), emul.solve_fast(rec, nfmax=80)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["stats"][:, 7], b["stats"][:, 7])
+    assert np.abs(a["u"] - b["u"]).max() < 1e-9
+    # the case is only meaningful if an active-set robot holds more than 64 rows (the capacity 80 foot-steps alone give)
+    rows = []
+    for i in range(rec.B):
+        ct = gait_ref.unpack_mask(a["mask"][i], rec.N)
+        y = a["y"][i]
+        fz_rows = sum(abs(y[12 * k + 3 * leg + 2]) > 1e-9 for k in range(rec.N) for leg in range(4) if ct[leg, k])
+        rows.append(int(fz_rows + (np.abs(y[12 * rec.N:]) > 1e-9).sum()))
+    assert max(r for r, path in zip(rows, a["stats"][:, 7]) if path == 1) > 64, rows
