@@ -51,6 +51,19 @@ def dynamics_matrix(Ad, Bd):
     return sp.hstack([I + shift @ big_minus_Ad, big_minus_Bd]).tocsc()
 
 
+def structural_pattern(N):
+    """Boolean (28N x 24N) pattern of the constraint matrix as the reference creates it (``self.A_sp``,
+    centroidal_mpc.py:203-209): identity + dense -Ad blocks on the sub-diagonal, dense -Bd blocks, friction rows."""
+    pat = np.zeros((28 * N, 24 * N), dtype=bool)
+    for k in range(N):
+        pat[12 * k:12 * k + 12, 12 * k:12 * k + 12] |= np.eye(12, dtype=bool)
+        if k >= 1:
+            pat[12 * k:12 * k + 12, 12 * (k - 1):12 * k] = True
+        pat[12 * k:12 * k + 12, 12 * N + 12 * k:12 * N + 12 * k + 12] = True
+    pat[12 * N:, :] = friction_matrix(N).toarray() != 0
+    return pat
+
+
 def build(Ad, Bd, gd, x0, x_ref, contact, Q=COST_Q, R=COST_R, mu=MU, fz_min=FZ_MIN):
     """Return dict(H, g, A, lba, uba, lbx, ubx) for one robot, reference ordering.
 
@@ -69,8 +82,12 @@ def build(Ad, Bd, gd, x0, x_ref, contact, Q=COST_Q, R=COST_R, mu=MU, fz_min=FZ_M
     # g = [vec_colmajor(-2 Q x_ref); 0]  (centroidal_mpc.py:248-253)
     g = np.concatenate([(-2.0 * (Q[:, None] * x_ref)).reshape(-1, order="F"), np.zeros(N * NU)])
     A = sp.vstack([dynamics_matrix(Ad, Bd), friction_matrix(N, mu)]).tocsc()
-    # beq (centroidal_mpc.py:257-261)
-    beq = np.concatenate([Ad @ x0 + gd] + [gd] * (N - 1))
+    # beq (centroidal_mpc.py:257-261); the 12-term products are accumulated in ascending column order with separately
+    # rounded multiply and add, the order of CasADi's dense mtimes (column-by-column axpy)
+    first = np.zeros(12)
+    for r in range(12):
+        first = first + Ad[:, r] * x0[r]
+    beq = np.concatenate([first + gd] + [gd] * (N - 1))
     # friction bounds: (-inf, 0] stance, (-inf, +inf) swing; row order k-major, leg, face (:264-279)
     u_ineq = np.full(16 * N, np.inf)
     for k in range(N):
