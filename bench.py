@@ -136,12 +136,63 @@ def cpu_baseline(rec, budget_s=15.0, eps=1e-5):
                       f"reference binary (CasADi/OSQP not installable)"}
 
 
+def _live_worker(job):
+    """One process of the live reference arm: solve robots [lo, hi) of the seeded workload, cold start."""
+    lo, hi, stress, reps = job
+    from convex_mpc_b200 import records
+    from oracle import live_reference
+    live = live_reference.LiveReference(eps=1e-5)
+    rec = records.random_records(65536, seed=65536, stress=stress).slice(lo, hi)
+    live.solve(rec, 0)                                   # solver construction outside the timers, as in the reference
+    t = time.perf_counter()
+    for _ in range(reps):
+        for b in range(rec.B):
+            live.solve(rec, b)
+    return time.perf_counter() - t
+
+
+def run_reference_live(args, cores):
+    """The reference's own CentroidalMPC (CasADi -> OSQP, eps 1e-5) on the first robots of the workload: once
+    single-process and once one process per core (CPU-1 / CPU-P)."""
+    import multiprocessing as mp
+    t1 = _live_worker((0, 8, args.stress, 1))
+    rate1 = 8 / t1
+    step_s = min(2.0, 90.0 / max(1, args.steps + args.warmup))
+    per_proc = int(max(1, rate1 * step_s))
+    jobs = [(i * per_proc, (i + 1) * per_proc, args.stress, args.steps) for i in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        ts = pool.map(_live_worker, jobs)
+    el = max(ts)
+    per_step = per_proc * cores
+    val = per_step * args.steps / el
+    sample = (f"{per_step} QPs per step ({per_proc} per process x {cores} processes, first robots of the 65536-robot "
+              f"workload), cold start, the reference's CentroidalMPC.solve_QP (CasADi conic -> OSQP) at eps 1e-5; "
+              f"single process: {rate1:.1f} QPs/s")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "horizon": 16, "start": "cold", "sample_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                         "value_1process": rate1},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU arm alone, rank 0 only."""
+    """--impl reference: the CPU arm alone, rank 0 only.  The reference's own CasADi -> OSQP path when the casadi
+    wheel and the reference tree are present (oracle/live_reference.py), else the restated port."""
     if rank != 0:
         return
     from convex_mpc_b200 import records
-    from oracle import cpu_port
+    from oracle import cpu_port, live_reference
+    if live_reference.available():
+        cores_l = os.cpu_count() or 1
+        try:
+            cores_l = len(os.sched_getaffinity(0))
+        except Exception:
+            pass
+        return run_reference_live(args, cores_l)
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
