@@ -25,6 +25,8 @@ PROTOTYPES = {
     "cmpc_set_max_stance": (c_int, [c_void_p, c_int]),
     "cmpc_set_generic": (c_int, [c_void_p, c_int]),
     "cmpc_set_prepass": (c_int, [c_void_p, c_int]),
+    "cmpc_workspace_bytes": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "cmpc_reserve": (c_int, [c_void_p, c_int]),
     "cmpc_contact_table": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, c_double, c_dp,
                                    c_void_p, c_void_p]),
     "cmpc_generate_traj": (c_int, [c_int, c_int, c_int] + [c_void_p] * 5 + [c_double, c_double, c_double, c_dp, c_dp] +

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cmpc.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "cmpc_core.cuh"), os.path.join(HERE, "csrc", "cmpc_fast.cuh"),
-        os.path.join(HERE, "csrc", "cmpc_riccati.cuh"), os.path.join(HERE, "csrc", "cmpc_riccati2.cuh"), os.path.join(HERE, "csrc", "cmpc_traj.cuh"),
+        os.path.join(HERE, "csrc", "cmpc_riccati.cuh"), os.path.join(HERE, "csrc", "cmpc_riccati2.cuh"), os.path.join(HERE, "csrc", "cmpc_traj.cuh"), os.path.join(HERE, "csrc", "cmpc_wrench.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "cmpc.h")]
 LIB = os.path.join(HERE, "libcmpc.so")
 

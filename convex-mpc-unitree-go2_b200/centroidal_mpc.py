@@ -139,7 +139,8 @@ class CentroidalMPC:
                   (generic kernel); "traj" / "device" force one
       eps_abs, eps_rel, max_iter, polish, check_termination, adaptive_rho_interval, rho0, sigma, alpha
       max_stance  upper bound on stance foot-steps per robot (see cmpc_set_max_stance)
-      prepass     Riccati pre-pass ahead of the condensed kernel: 0 off, 1/2/3 = versions (default 3; cmpc_set_prepass)
+      prepass     pre-pass ahead of the condensed kernel: 0 off, 1/2/3 = Riccati sweeps for nominal robots, 4 (default) =
+                  wrench-space projected Riccati + primal-dual active set for all robots (cmpc_set_prepass)
       generic_kernel  diagnostics: solve raw-input batches with the generic kernel (the one that serves
                   caller-supplied Ad/Bd/gd) instead of the closed-form fast kernel
     """
@@ -147,7 +148,7 @@ class CentroidalMPC:
     def __init__(self, go2, traj, *, device=None, mode="active_set", dynamics="auto", max_batch=None,
                  eps_abs=None, eps_rel=None, max_iter=None, polish=None, check_termination=None,
                  adaptive_rho_interval=None, rho0=1e-4, sigma=1e-6, alpha=1.6, mu=MU, fz_min=FZ_MIN,
-                 Q=None, R=None, max_stance=None, generic_kernel=False, prepass=3, verbose=True):
+                 Q=None, R=None, max_stance=None, generic_kernel=False, prepass=4, verbose=True):
         if not torch.cuda.is_available():
             raise _lib.CmpcError("CentroidalMPC needs a CUDA device (no CPU fallback)")
         self._lib = _lib.load()

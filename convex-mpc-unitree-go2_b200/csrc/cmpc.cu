@@ -24,6 +24,7 @@
 #include "cmpc_riccati.cuh"
 #include "cmpc_riccati2.cuh"
 #include "cmpc_traj.cuh"
+#include "cmpc_wrench.cuh"
 
 using namespace cmpc;
 
@@ -297,6 +298,66 @@ riccati2_lockstep_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, in
     }
 }
 
+// Wrench-space projected Riccati + primal-dual active set (cmpc_wrench.cuh): four threads per robot, eight robots per
+// warp, persistent CTAs that take robots from a device cursor.  A quad keeps its robot until the working set has
+// settled (every sweep has the same length, so the eight robots of a warp stay in step whatever their iteration
+// counts are) and then takes the next one.  Robots it cannot finish (cycling working sets, budget) are appended to
+// the work-list of the condensed kernel.  ctl: [0] work-list length, [1] cursor of the condensed kernel, [2] robot cursor.
+constexpr int kWrThreads = 128;
+__global__ void __launch_bounds__(kWrThreads, 2)
+wrench_pdas_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, wr::D2* __restrict__ gains,
+                   int* __restrict__ worklist, int* __restrict__ ctl, size_t robot_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    wr::Tab* tb = reinterpret_cast<wr::Tab*>(smem);
+    if (threadIdx.x < 16) wr::fill_tab(*tb, p, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, qlane = threadIdx.x & 3, rslot = threadIdx.x >> 2;
+    const size_t tab_bytes = (sizeof(wr::Tab) + 15) & ~(size_t)15;
+    wr::Sh* sh = reinterpret_cast<wr::Sh*>(smem + tab_bytes + (size_t)rslot * robot_bytes);
+    unsigned char* codes = wr::codes_of(sh);
+    const int N = bi.N;
+    wr::TS ts[1];
+    wr::Env e;
+    e.p = &p; e.tb = tb;
+    e.gains = gains + (size_t)blockIdx.x * N * wr::GAIN_D2 * blockDim.x + threadIdx.x;
+    e.gstride = blockDim.x;
+    e.dt = bi.dt; e.h = bi.dt * bi.dt / 2.0;
+    e.in = qp_in(bi, 0);
+    e.o = qp_out(bo, 0, N);
+    const int max_it = p.pdas_max_iter;
+    int b = -1, it = 0, nst = 0;
+    bool exhausted = false;
+    for (;;) {
+        const bool need = (b < 0) && !exhausted;
+        int nb = -1;
+        if (need && qlane == 0) nb = atomicAdd(ctl + 2, 1);
+        nb = __shfl_sync(0xffffffffu, nb, lane & ~3);
+        bool fresh = false;
+        if (need) {
+            if (nb < B) { b = nb; it = 0; fresh = true; e.in = qp_in(bi, b); e.o = qp_out(bo, b, N); }
+            else exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, b >= 0)) break;
+        const int n2 = wr::init_robot(qlane, fresh, ts, sh, e, warm);
+        if (fresh) nst = n2;
+        bool fail = fresh && (nst == 0 || nst > nfmax);          // nothing to optimise / over the stance bound: condensed kernel reports
+        const bool valid = (b >= 0) && !fail;
+        const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
+        unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
+        const unsigned char* prev = codes + (size_t)((it + 2) % 3) * 4 * N;
+        const double pmin = wr::backward_sweep(qlane, ts, sh, e, cur);
+        const int fl = wr::forward_sweep(qlane, valid, ts, sh, e, cur, prev, next);
+        const bool conv = valid && (pmin > 0.0) && !(fl & 1);
+        if (valid && !conv && (!(pmin > 0.0) || (fl & 2) || it + 1 >= max_it)) fail = true;
+        if (__any_sync(0xffffffffu, conv)) {
+            const int ok = wr::epilogue(qlane, conv, ts, sh, e, cur, nst, it + 1, warm);
+            if (conv && !ok) fail = true;
+        }
+        if (fail && qlane == 0) worklist[atomicAdd(ctl, 1)] = b;
+        if (conv || fail) b = -1; else if (valid) ++it;
+    }
+}
+
 // Batched ComTraj.generate_traj (cmpc_traj.cuh): one thread per (robot, leg).
 __global__ void generate_traj_kernel(int B, int N, const double* __restrict__ x0, const double* __restrict__ R_wb,
                                      const double* __restrict__ lever, const double* __restrict__ cmd,
@@ -456,19 +517,26 @@ struct cmpc_handle {
     int sm_count = 148;
     size_t smem_optin = 0, smem_per_sm = 0;
     Params p;
-    int prepass = 3;       // Riccati pre-pass ahead of the condensed kernel (active-set mode, raw inputs): 0 off, 1 v1, 2 v2, 3 v2 lock-step
-    // pre-pass slots (work-list, its counter, gain scratch); calls rotate over them so that solves enqueued on
-    // different streams do not share one
+    int prepass = 4;       // pre-pass ahead of the condensed kernel (active-set mode, raw inputs): 0 off, 1-3 Riccati sweeps of round 1, 4 wrench-space PDAS
     int prepass_min_batch = 2048;   // CMPC_PREPASS_MIN_BATCH overrides (diagnostics)
-    struct PreSlot { int* worklist = nullptr; int* count = nullptr; double* gains = nullptr; int cap = 0; size_t gain_doubles = 0; };
-    PreSlot pre[4];
-    unsigned pre_next = 0;
-    double* yg_scratch = nullptr;   // per-CTA rows of large working sets (kcap x npad doubles each)
-    size_t yg_stride = 0;
-    int yg_ctas = 0;
-    double* hp_scratch = nullptr;   // packed-matrix scratch when it does not fit shared memory
-    size_t hp_stride = 0;
-    int hp_ctas = 0;
+    // Workspace.  Everything a solve needs beyond its arguments lives in one of four SLOTS (work-list, counters, gain
+    // scratch, L2-resident scratch of the condensed kernel); consecutive calls rotate over the slots, so up to four
+    // solves of one handle may be in flight on different streams.  Slots are sized by cmpc_reserve (or by the first
+    // solve, for max_batch robots); nothing is allocated afterwards.
+    struct Slot {
+        int* worklist = nullptr; int* ctl = nullptr;          // ctl: [0] work-list length, [1] cursor of the condensed kernel, [2] robot cursor of the wrench kernel
+        double* gains = nullptr; size_t gain_bytes = 0;       // Riccati gains (pre-pass 1-3) or wrench gains (pre-pass 4)
+        double* yg = nullptr;                                 // rows of large working sets, per CTA of the condensed kernel
+        double* hp = nullptr;                                 // block-packed factor when it does not fit shared memory
+    };
+    Slot slot[4];
+    std::atomic<unsigned> slot_next{0};
+    int reserved_batch = 0;         // robots the slots are sized for (0 = not reserved yet)
+    int reserved_nfmax = 0;
+    size_t yg_stride = 0, hp_stride = 0, hp_stride_generic = 0;
+    size_t reserved_bytes = 0;
+    // cudaFuncSetAttribute is issued only when the dynamic shared-memory size of a kernel changes
+    size_t attr_fast[2] = {0, 0}, attr_generic = 0, attr_build = 0, attr_ric[3] = {0, 0, 0}, attr_wrench = 0;
     // device-resident state for the *_host entry
     struct HostPath {
         bool ready = false;
@@ -507,26 +575,11 @@ size_t smem_needed(int N, int nfmax, bool hp_external) {
     return ws_carve(w, base, N, nfmax, hp_external ? &dummy : nullptr);
 }
 
-// Decide where the packed matrix lives and make sure scratch exists.  Returns smem bytes.
-int plan_launch(cmpc_handle* h, int nfmax, const void* kernel, size_t* smem_out, double** hp, size_t* stride, int* grid_cap) {
-    size_t need = smem_needed(h->N, nfmax, false);
-    *hp = nullptr; *stride = 0; *grid_cap = 0;
-    if (need > h->smem_optin) {
-        need = smem_needed(h->N, nfmax, true);
-        if (need > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
-        const size_t nmax = 3 * (size_t)nfmax;
-        const size_t st = ((nmax + 1) * (nmax + 2) / 2 + 1) & ~(size_t)1;
-        const int ctas = h->sm_count * 2;
-        if (h->hp_stride < st || h->hp_ctas < ctas) {
-            if (h->hp_scratch) cudaFree(h->hp_scratch);
-            h->hp_scratch = nullptr;
-            CU_TRY(cudaMalloc(&h->hp_scratch, st * ctas * sizeof(double)));
-            h->hp_stride = st; h->hp_ctas = ctas;
-        }
-        *hp = h->hp_scratch; *stride = h->hp_stride; *grid_cap = h->hp_ctas;
-    }
+// cudaFuncSetAttribute only when the size changes (the call is not free and is not capturable)
+int set_smem(const void* kernel, size_t need, size_t* cached) {
+    if (*cached == need) return 0;
     CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    *smem_out = need;
+    *cached = need;
     return 0;
 }
 
@@ -537,38 +590,87 @@ size_t smem_needed_fast(int N, int nfmax, bool hb_external) {
     return fast::ws_carve_fast(w, base, N, nfmax, hb_external ? &dummy : nullptr);
 }
 
-// Fast path: where the block-packed matrix lives, shared-memory bytes, and the grid.
-int plan_launch_fast(cmpc_handle* h, int nfmax, int B, size_t* smem_out, double** hb, size_t* stride, int* grid) {
-    size_t need = smem_needed_fast(h->N, nfmax, false);
-    *hb = nullptr; *stride = 0;
-    int per_sm = 1;
-    if (need > h->smem_optin) {
-        need = smem_needed_fast(h->N, nfmax, true);
-        if (need > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
-        const size_t nblk = (3 * (size_t)nfmax + 7) / 8;
-        const size_t st = nblk * (nblk + 1) / 2 * 64;
-        const int ctas = h->sm_count * 2;
-        if (h->hp_stride < st || h->hp_ctas < ctas) {
-            if (h->hp_scratch) cudaFree(h->hp_scratch);
-            h->hp_scratch = nullptr;
-            CU_TRY(cudaMalloc(&h->hp_scratch, st * ctas * sizeof(double)));
-            h->hp_stride = st; h->hp_ctas = ctas;
-        }
-        *hb = h->hp_scratch; *stride = h->hp_stride;
-        per_sm = 2;
-    } else {
-        // CTAs per SM by shared memory (1 KB per CTA is reserved by the system)
-        per_sm = (int)(h->smem_per_sm / (need + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;      // register file: 256 threads x 128 registers x 2
-        if (const char* e = getenv("CMPC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // diagnostics
+// per-CTA strides (doubles) of the global scratch the kernels may need, 0 if they do not need it
+size_t hp_stride_generic(const cmpc_handle* h, int nfmax) {
+    if (smem_needed(h->N, nfmax, false) <= h->smem_optin) return 0;
+    const size_t nmax = 3 * (size_t)nfmax;
+    return ((nmax + 1) * (nmax + 2) / 2 + 1) & ~(size_t)1;
+}
+size_t hp_stride_fast(const cmpc_handle* h, int nfmax) {
+    if (smem_needed_fast(h->N, nfmax, false) <= h->smem_optin) return 0;
+    const size_t nblk = (3 * (size_t)nfmax + 7) / 8;
+    return nblk * (nblk + 1) / 2 * 64;
+}
+size_t yg_stride_of(const cmpc_handle* h, int nfmax) {
+    const size_t npad = ((3 * (size_t)nfmax + 7) / 8) * 8;
+    return (size_t)fast::kcap_fast(nfmax, h->N) * npad;
+}
+
+// wrench kernel: shared memory per CTA and the grid for B robots
+size_t wrench_smem(const cmpc_handle* h) {
+    return ((sizeof(wr::Tab) + 15) & ~(size_t)15) + (size_t)(kWrThreads / 4) * wr::robot_bytes(h->N);
+}
+int wrench_grid(const cmpc_handle* h, int B) {
+    int per_sm = (int)(h->smem_per_sm / (wrench_smem(h) + 1024));
+    if (per_sm > 2) per_sm = 2;                      // 255 registers x 128 threads x 2
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = getenv("CMPC_WRENCH_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // diagnostics
+    const int want = (B + kWrThreads / 4 - 1) / (kWrThreads / 4), cap = h->sm_count * per_sm;
+    return want < cap ? want : cap;
+}
+
+struct SlotSizes { size_t worklist, ctl, gains, yg, hp, total; };
+SlotSizes slot_sizes(const cmpc_handle* h, int B) {
+    SlotSizes z;
+    const int ctas = h->sm_count * 2;
+    z.worklist = (size_t)B * sizeof(int);
+    z.ctl = 4 * sizeof(int);
+    const size_t g_ric = ric::gain_doubles(h->nfmax) * (size_t)h->sm_count * 32 * sizeof(double);    // up to 32 robots in flight per SM
+    const size_t g_wr = (size_t)h->sm_count * 2 * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2);
+    z.gains = g_ric > g_wr ? g_ric : g_wr;
+    z.yg = yg_stride_of(h, h->nfmax) * ctas * sizeof(double);
+    size_t hs = hp_stride_fast(h, h->nfmax);
+    const size_t hg = hp_stride_generic(h, h->nfmax), hb = hp_stride_generic(h, 4 * h->N);
+    if (hg > hs) hs = hg;
+    if (hb > hs) hs = hb;
+    z.hp = hs * ctas * sizeof(double);
+    z.total = 4 * (z.worklist + z.ctl + z.gains + z.yg + z.hp);
+    return z;
+}
+
+void free_slots(cmpc_handle* h) {
+    for (auto& q : h->slot) {
+        void* ptrs[] = {q.worklist, q.ctl, q.gains, q.yg, q.hp};
+        for (void* p : ptrs) if (p) cudaFree(p);
+        q = cmpc_handle::Slot();
     }
-    if (*hb) CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    else CU_TRY(cudaFuncSetAttribute((const void*)solve_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    *smem_out = need;
-    const int cap = h->sm_count * per_sm;
-    *grid = B < cap ? B : cap;
+    h->reserved_batch = 0;
+    h->reserved_bytes = 0;
+}
+
+// (Re)size the four slots for batches of up to B robots with the current stance bound.  Synchronises the device when
+// it has to free; not to be called while a graph is being captured.
+int reserve_slots(cmpc_handle* h, int B) {
+    if (B <= h->reserved_batch && h->nfmax == h->reserved_nfmax) return 0;
+    if (h->reserved_batch) { CU_TRY(cudaDeviceSynchronize()); free_slots(h); }
+    const SlotSizes z = slot_sizes(h, B);
+    for (auto& q : h->slot) {
+        CU_TRY(cudaMalloc(&q.worklist, z.worklist));
+        CU_TRY(cudaMalloc(&q.ctl, z.ctl));
+        CU_TRY(cudaMalloc(&q.gains, z.gains));
+        q.gain_bytes = z.gains;
+        if (z.yg) CU_TRY(cudaMalloc(&q.yg, z.yg));
+        if (z.hp) CU_TRY(cudaMalloc(&q.hp, z.hp));
+    }
+    h->reserved_batch = B;
+    h->reserved_nfmax = h->nfmax;
+    h->reserved_bytes = z.total;
     return 0;
+}
+
+int ensure_reserved(cmpc_handle* h, int B) {
+    if (B <= h->reserved_batch && h->nfmax == h->reserved_nfmax) return 0;
+    return reserve_slots(h, B > h->max_batch ? B : h->max_batch);
 }
 
 }  // namespace
@@ -587,17 +689,17 @@ int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
     if (N < 1 || N > 48) return fail("horizon N must be in [1, 48]");
     if (max_batch < 1) return fail("max_batch must be >= 1");
     CU_TRY(cudaSetDevice(device));
-    cmpc_handle* h = new cmpc_handle();
+    int sms = 0, optin = 0, per_sm = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CU_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    cmpc_handle* h = new cmpc_handle();      // nothing below can fail: no handle is ever leaked
     h->N = N; h->W = (4 * N + 63) / 64; h->max_batch = max_batch; h->device = device;
     h->nfmax = 4 * N;
     default_params(h->p);
-    int v = 0;
-    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
-    h->sm_count = v;
-    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    h->smem_optin = (size_t)v;
-    CU_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
-    h->smem_per_sm = (size_t)v;
+    h->sm_count = sms;
+    h->smem_optin = (size_t)optin;
+    h->smem_per_sm = (size_t)per_sm;
     if (const char* e = getenv("CMPC_PREPASS_MIN_BATCH")) { const int mb = atoi(e); if (mb >= 1) h->prepass_min_batch = mb; }
     if (const char* e = getenv("CMPC_PDAS_MAX_ITER")) { const int v = atoi(e); if (v >= 1) h->p.pdas_max_iter = v; }   // tuning
     *out = h;
@@ -607,9 +709,7 @@ int cmpc_create(int N, int max_batch, int device, cmpc_handle** out) {
 int cmpc_destroy(cmpc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->hp_scratch) cudaFree(h->hp_scratch);
-    if (h->yg_scratch) cudaFree(h->yg_scratch);
-    for (auto& ps : h->pre) { if (ps.worklist) cudaFree(ps.worklist); if (ps.count) cudaFree(ps.count); if (ps.gains) cudaFree(ps.gains); }
+    free_slots(h);
     auto& q = h->hp;
     void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -645,7 +745,7 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
 
 int cmpc_set_prepass(cmpc_handle* h, int on) {
     if (!h) return fail("null handle");
-    h->prepass = on < 0 ? 0 : (on > 3 ? 3 : on);      // 0 off, 1 reference sweep (one robot per warp), 2 register-resident sweep, 3 = 2 in lock-step
+    h->prepass = on < 0 ? 0 : (on > 4 ? 4 : on);      // 0 off, 1-3 Riccati sweeps of round 1 (nominal robots only), 4 wrench-space PDAS (default)
     return 0;
 }
 
@@ -732,6 +832,7 @@ int cmpc_stance_torque(int device, int N, int B, const double* J_foot_world, con
 
 int cmpc_pack_contact(cmpc_handle* h, int B, const int32_t* table, uint64_t* mask_out, void* stream) {
     if (!h || !table || !mask_out) return fail("null argument");
+    if (B < 0) return fail("negative batch");
     if (B == 0) return 0;
     CU_TRY(cudaSetDevice(h->device));
     const int tpb = 128;
@@ -744,6 +845,7 @@ int cmpc_pack_contact(cmpc_handle* h, int B, const int32_t* table, uint64_t* mas
 int cmpc_dynamics(cmpc_handle* h, int B, const double* x_ref, const double* r_foot, const double* I_world,
                   const double* mass, double dt, double* Ad, double* Bd, double* gd, void* stream) {
     if (!h || !x_ref || !r_foot || !I_world || !mass || !Ad || !Bd || !gd) return fail("null argument");
+    if (B < 0) return fail("negative batch");
     if (B == 0) return 0;
     CU_TRY(cudaSetDevice(h->device));
     const int tpb = 128, total = B * h->N;
@@ -768,16 +870,37 @@ int cmpc_build(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                double* H, double* g, void* stream) {
     if (!h || !H || !g) return fail("null argument");
     if (check_inputs(Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass)) return -1;
+    if (B < 0) return fail("negative batch");
     if (B == 0) return 0;
     CU_TRY(cudaSetDevice(h->device));
+    if (ensure_reserved(h, B)) return -1;
     BatchIn bi{Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, nullptr, h->N, h->W};
-    size_t smem; double* hp; size_t stride; int cap;
-    if (plan_launch(h, 4 * h->N, (const void*)build_kernel, &smem, &hp, &stride, &cap)) return -1;
-    const int grid = cap ? (B < cap ? B : cap) : B;
-    build_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, B, 4 * h->N, H, g, hp, stride);
+    const size_t stride = hp_stride_generic(h, 4 * h->N);
+    const size_t smem = smem_needed(h->N, 4 * h->N, stride != 0);
+    if (smem > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
+    if (set_smem((const void*)build_kernel, smem, &h->attr_build)) return -1;
+    auto& sl = h->slot[h->slot_next.fetch_add(1) & 3u];
+    const int cap = h->sm_count * 2;
+    const int grid = stride ? (B < cap ? B : cap) : B;
+    build_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, B, 4 * h->N, H, g, stride ? sl.hp : nullptr, stride);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;
+}
+
+int cmpc_workspace_bytes(cmpc_handle* h, int B, size_t* bytes) {
+    if (!h || !bytes) return fail("null argument");
+    if (B < 1) return fail("batch must be >= 1");
+    *bytes = slot_sizes(h, B).total;
+    return 0;
+}
+
+int cmpc_reserve(cmpc_handle* h, int B) {
+    if (!h) return fail("null handle");
+    if (B < 1) return fail("batch must be >= 1");
+    CU_TRY(cudaSetDevice(h->device));
+    if (B > h->max_batch) h->max_batch = B;
+    return reserve_slots(h, B);
 }
 
 int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd, const double* x0,
@@ -789,50 +912,55 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
     if (B < 0) return fail("negative batch");
     if (B == 0) return 0;
     CU_TRY(cudaSetDevice(h->device));
+    if (ensure_reserved(h, B)) return -1;         // allocates only before cmpc_reserve / the first solve
+    cudaStream_t st = (cudaStream_t)stream;
     BatchIn bi{Ad, Bd, gd, x0, x_ref, r_foot, I_world, mass, dt, mask, h->N, h->W};
     BatchOut bo{u, y, rho, X, nu, status, iters, stats};
-    size_t smem; double* hp; size_t stride; int cap;
+    // every in-flight solve owns one slot: work-list, counters, gains and the L2-resident scratch of the condensed
+    // kernel are never shared between solves enqueued on different streams
+    auto& sl = h->slot[h->slot_next.fetch_add(1) & 3u];
     if (!Ad && !h->force_generic) {
-        // raw inputs: v2 fast path (closed-form build, block-packed DMMA factorisation)
-        int grid_f = 0;
-        if (plan_launch_fast(h, h->nfmax, B, &smem, &hp, &stride, &grid_f)) return -1;
+        // raw inputs: closed-form dynamics on the device
+        const size_t hstride = hp_stride_fast(h, h->nfmax);
+        const size_t smem = smem_needed_fast(h->N, h->nfmax, hstride != 0);
+        if (smem > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
+        int per_sm = 2;
+        if (!hstride) {
+            per_sm = (int)(h->smem_per_sm / (smem + 1024));      // 1 KB per CTA is reserved by the system
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 2) per_sm = 2;                           // register file: 256 threads x 128 registers x 2
+            if (const char* e = getenv("CMPC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // diagnostics
+        }
+        if (hstride) { if (set_smem((const void*)solve_fast_kernel<true>, smem, &h->attr_fast[1])) return -1; }
+        else if (set_smem((const void*)solve_fast_kernel<false>, smem, &h->attr_fast[0])) return -1;
+        int grid_f = h->sm_count * per_sm;
+        if (B < grid_f) grid_f = B;
         const int* wl = nullptr;
         const int* wlc = nullptr;
         // small batches are latency-bound (fewer robots than CTA slots x a few rounds): the extra kernel in front only
         // adds to the latency there (batch 1: 45 -> 99 us), so the pre-pass starts at prepass_min_batch robots
         if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET && B >= h->prepass_min_batch) {
-            // Riccati pre-pass: finishes the robots without an active constraint, lists the others
-            ric::WsR wr;
-            const size_t per_warp = (ric::ws_carve_ric(wr, reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20)), h->N) + 15) & ~(size_t)15;
-            const int wpb = kRicThreads / 32;
-            const size_t smem_r = per_warp * wpb;
-            if (smem_r <= h->smem_optin) {
-                int per_sm = (int)(h->smem_per_sm / (smem_r + 1024));
-                if (per_sm > 3) per_sm = 3;
-                if (per_sm < 1) per_sm = 1;
-                const int want = (B + wpb - 1) / wpb, cap = h->sm_count * per_sm;
-                const int grid_r = want < cap ? want : cap;
-                const size_t gd = ric::gain_doubles(h->nfmax);
-                const size_t need_g = gd * (size_t)h->sm_count * 32;          // up to 32 robots in flight per SM (v2)
-                // all four slots are (re)sized together, on the first call that needs it: later calls -- including
-                // calls made while a CUDA graph is being captured -- allocate nothing
-                for (auto& q : h->pre) {
-                    if (q.cap < B) {
-                        if (q.worklist) cudaFree(q.worklist);
-                        q.worklist = nullptr;
-                        CU_TRY(cudaMalloc(&q.worklist, (size_t)B * sizeof(int)));
-                        q.cap = B;
-                    }
-                    if (!q.count) CU_TRY(cudaMalloc(&q.count, 2 * sizeof(int)));      // [0] work-list length, [1] cursor of the condensed kernel
-                    if (q.gain_doubles < need_g) {
-                        if (q.gains) cudaFree(q.gains);
-                        q.gains = nullptr;
-                        CU_TRY(cudaMalloc(&q.gains, need_g * sizeof(double)));
-                        q.gain_doubles = need_g;
-                    }
+            CU_TRY(cudaMemsetAsync(sl.ctl, 0, 4 * sizeof(int), st));
+            bool launched = false;
+            if (h->prepass == 4) {
+                // wrench-space projected Riccati + PDAS: finishes nominal and constrained robots alike; what it
+                // cannot finish (cycling working sets) goes to the condensed kernel through the work-list
+                const size_t smem_w = wrench_smem(h);
+                const int grid_w = wrench_grid(h, B);
+                if (smem_w <= h->smem_optin && (size_t)grid_w * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2) <= sl.gain_bytes) {
+                    if (set_smem((const void*)wrench_pdas_kernel, smem_w, &h->attr_wrench)) return -1;
+                    wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bi, bo, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
+                                                                         sl.worklist, sl.ctl, wr::robot_bytes(h->N));
+                    launched = true;
                 }
-                auto& ps = h->pre[h->pre_next++ & 3u];
-                CU_TRY(cudaMemsetAsync(ps.count, 0, 2 * sizeof(int), (cudaStream_t)stream));
+            }
+            if (!launched) {
+                // Riccati pre-pass of round 1: finishes the robots without an active constraint, lists the others
+                ric::WsR wr_;
+                const size_t per_warp = (ric::ws_carve_ric(wr_, reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(1 << 20)), h->N) + 15) & ~(size_t)15;
+                const int wpb = kRicThreads / 32;
+                const size_t smem_r = per_warp * wpb;
+                const size_t gd_ = ric::gain_doubles(h->nfmax);
                 const size_t per_half = ric2::half_bytes(h->N);
                 const int hpb = (kRic2Threads / 32) * 2;
                 const size_t smem_2 = per_half * hpb;
@@ -842,50 +970,51 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 int hpl = (int)(h->smem_optin / per_half) & ~1;
                 if (hpl > (kRic2LsThreads / 32) * 2) hpl = (kRic2LsThreads / 32) * 2;
                 const size_t smem_ls = per_half * (size_t)hpl;
-                if (h->prepass == 3 && hpl >= 4) {
+                const int mode = h->prepass == 4 ? 3 : h->prepass;
+                if (mode == 3 && hpl >= 4) {
                     const int want3 = (B + hpl - 1) / hpl;
-                    CU_TRY(cudaFuncSetAttribute((const void*)riccati2_lockstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ls));
-                    riccati2_lockstep_kernel<<<want3 < h->sm_count ? want3 : h->sm_count, 16 * hpl, smem_ls, (cudaStream_t)stream>>>(
-                        h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd, ps.worklist, ps.count, per_half);
-                } else if (h->prepass >= 2 && per_sm2 >= 1 && gd * (size_t)h->sm_count * per_sm2 * hpb <= ps.gain_doubles) {
+                    if (set_smem((const void*)riccati2_lockstep_kernel, smem_ls, &h->attr_ric[2])) return -1;
+                    riccati2_lockstep_kernel<<<want3 < h->sm_count ? want3 : h->sm_count, 16 * hpl, smem_ls, st>>>(
+                        h->p, bi, bo, B, h->nfmax, warm, sl.gains, gd_, sl.worklist, sl.ctl, per_half);
+                    launched = true;
+                } else if (mode >= 2 && per_sm2 >= 1 && gd_ * (size_t)h->sm_count * per_sm2 * hpb * sizeof(double) <= sl.gain_bytes) {
                     const int want2 = (B + hpb - 1) / hpb, cap2 = h->sm_count * per_sm2;
-                    CU_TRY(cudaFuncSetAttribute((const void*)riccati2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2));
-                    riccati2_kernel<<<want2 < cap2 ? want2 : cap2, kRic2Threads, smem_2, (cudaStream_t)stream>>>(
-                        h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd, ps.worklist, ps.count, per_half);
-                } else {
-                    CU_TRY(cudaFuncSetAttribute((const void*)riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-                    riccati_kernel<<<grid_r, kRicThreads, smem_r, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, ps.gains, gd,
-                                                                                      ps.worklist, ps.count, per_warp);
+                    if (set_smem((const void*)riccati2_kernel, smem_2, &h->attr_ric[1])) return -1;
+                    riccati2_kernel<<<want2 < cap2 ? want2 : cap2, kRic2Threads, smem_2, st>>>(
+                        h->p, bi, bo, B, h->nfmax, warm, sl.gains, gd_, sl.worklist, sl.ctl, per_half);
+                    launched = true;
+                } else if (smem_r <= h->smem_optin) {
+                    int per_sm_r = (int)(h->smem_per_sm / (smem_r + 1024));
+                    if (per_sm_r > 3) per_sm_r = 3;
+                    if (per_sm_r < 1) per_sm_r = 1;
+                    const int want = (B + wpb - 1) / wpb, cap_r = h->sm_count * per_sm_r;
+                    if (set_smem((const void*)riccati_kernel, smem_r, &h->attr_ric[0])) return -1;
+                    riccati_kernel<<<want < cap_r ? want : cap_r, kRicThreads, smem_r, st>>>(h->p, bi, bo, B, h->nfmax, warm, sl.gains, gd_,
+                                                                                          sl.worklist, sl.ctl, per_warp);
+                    launched = true;
                 }
+            }
+            if (launched) {
                 ++g_launches;
                 CU_TRY(cudaGetLastError());
-                wl = ps.worklist; wlc = ps.count;
+                wl = sl.worklist; wlc = sl.ctl;
                 const int cap_f = h->sm_count * 2;
                 grid_f = B < cap_f ? B : cap_f;
             }
         }
-        {   // global scratch for the rows of working sets that do not fit shared memory (allocated once)
-            const size_t npad = ((3 * (size_t)h->nfmax + 7) / 8) * 8;
-            const size_t st = (size_t)fast::kcap_fast(h->nfmax, h->N) * npad;
-            const int ctas = h->sm_count * 2;
-            if (h->yg_stride < st || h->yg_ctas < ctas) {
-                if (h->yg_scratch) cudaFree(h->yg_scratch);
-                h->yg_scratch = nullptr;
-                CU_TRY(cudaMalloc(&h->yg_scratch, st * ctas * sizeof(double)));
-                h->yg_stride = st; h->yg_ctas = ctas;
-            }
-        }
-        if (hp) solve_fast_kernel<true><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc,
-                                                                                          h->yg_scratch, h->yg_stride);
-        else solve_fast_kernel<false><<<grid_f, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride, wl, wlc,
-                                                                                           h->yg_scratch, h->yg_stride);
+        if (hstride) solve_fast_kernel<true><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, sl.hp, hstride, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
+        else solve_fast_kernel<false><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, nullptr, 0, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
         ++g_launches;
         CU_TRY(cudaGetLastError());
         return 0;
     }
-    if (plan_launch(h, h->nfmax, (const void*)solve_kernel, &smem, &hp, &stride, &cap)) return -1;
-    const int grid = cap ? (B < cap ? B : cap) : B;
-    solve_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(h->p, bi, bo, B, h->nfmax, warm, hp, stride);
+    const size_t stride = hp_stride_generic(h, h->nfmax);
+    const size_t smem = smem_needed(h->N, h->nfmax, stride != 0);
+    if (smem > h->smem_optin) return fail("workspace does not fit shared memory even with the matrix in global memory");
+    if (set_smem((const void*)solve_kernel, smem, &h->attr_generic)) return -1;
+    const int cap = h->sm_count * 2;
+    const int grid = stride ? (B < cap ? B : cap) : B;
+    solve_kernel<<<grid, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, stride ? sl.hp : nullptr, stride);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -963,6 +1092,8 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
 /* stats of the last cmpc_solve_host call stay on the device; copy them out on request */
 int cmpc_host_stats(cmpc_handle* h, int B, double* stats_host) {
     if (!h || !stats_host || !h->hp.ready) return fail("no host-path state");
+    if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");
+    if (B == 0) return 0;
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaMemcpy(stats_host, h->hp.stats, (size_t)B * CMPC_NSTAT * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;

@@ -1,0 +1,786 @@
+// cmpc_wrench.cuh -- wrench-space projected Riccati + primal-dual active set: the whole QP of
+// centroidal_mpc.py:69-120 (build + CasADi->OSQP solve) for one robot on FOUR threads ("quad"), eight robots per
+// warp, every robot / stance pattern / working set running the same straight-line code.
+//
+// Structure used (NumPy twin with the derivation: oracle/wrench_riccati.py):
+//   * B_d[k] = Bbar [C_1 .. C_4],  C_j = [I; W_j],  W_j = I_world^-1 [r_j]x  (com_trajectory.py:234-262): the forces
+//     act on the state only through the 6-dimensional wrench  w = sum_j C_j f_j,
+//       Bbar = [[h/m I, 0], [0, h Rz'], [dt/m I, 0], [0, dt I]],   h = dt^2/2,   A = I + dt E.
+//   * Every inequality row (fz >= fz_min centroidal_mpc.py:163-170, friction faces :324-359, swing forces = 0
+//     :150-161) touches one foot at one step, so a working set is eliminated foot by foot:
+//       f_j = fhat_j - Pi_j C_j' mu,   Pi_j = Z (Z'RZ)^-1 Z' = diag(dx, dy, 0) + sg z z'   (0 for swing / pinned feet)
+//     and the stage enters the recursion only through  Lam_k = sum_j C_j Pi_j C_j'  (6 x 6)  and  what_k = sum_j C_j fhat_j.
+//   * Backward stage (cost-to-go x'Px + 2p'x, all factorizations 6 x 6):
+//       Gbar = Bbar'P Bbar = L L',   Nn = I + L' Lam L = Ln Ln',   Phi = L^-T (I - Nn^-1) L^-1,   Gam = L Nn^-1 L^-1
+//       P  <- Q + A'(P - (P Bbar) Phi (P Bbar)') A,      p <- -Q xref + A'(q - (P Bbar) Phi Bbar'q),   q = P ghat + p
+//       mu_k = Ktil (A x_k) + kbar,   Ktil = Gam (P Bbar)',   kbar = Gam Bbar'q            (wrench co-state)
+//   * Primal-dual active set: after the forward sweep every foot-step gets multipliers from its own 3 x 3 stationarity
+//     system and the next working set is { rows with lam + violation > 0 } (the rule of solve_active_set_fast); the
+//     loop ends when the set repeats.  A sweep costs the same whatever the size of the working set.
+//
+// Thread a of a quad owns the block row a in {p, rpy, v, omega} of P (3 x 12, registers) and, in its second role,
+// foot a.  Exchanges inside the quad go through ~1.6 KB of shared memory per robot and __syncwarp; the 6 x 6 work is
+// done redundantly by the four threads (no exchange, no idle lanes).  Gains go to an L2-resident scratch.
+// The same source compiles for the host (tests/_emul): there the four threads of a quad run one after the other
+// between the synchronisation points.
+#pragma once
+#include "cmpc_core.cuh"
+
+namespace cmpc {
+namespace wr {
+
+enum { PATH_WRENCH = 5 };
+constexpr unsigned char SWING = 255;
+constexpr int GAIN_D2 = 12;      // double2 slots per thread and stage: Ktil rows (9), kbar part (1), state (2)
+
+#if defined(__CUDA_ARCH__)
+#define WR_Q_BEGIN { const int q = qlane; TS& t = ts[0];
+#define WR_Q_END }
+#define WR_SYNC() __syncwarp()
+#define WR_NTS 1
+#define WR_GQ 0          // e.gains already points at this thread's slots
+#else
+#define WR_Q_BEGIN for (int q = 0; q < 4; ++q) { TS& t = ts[q];
+#define WR_Q_END }
+#define WR_SYNC() ((void)0)
+#define WR_NTS 4
+#define WR_GQ q
+#endif
+
+struct alignas(16) D2 { double x, y; };
+
+// CTA-wide tables (shared memory): indices depend on the thread, so they must not sit in the constant bank
+struct Tab {
+    double Q[12], R[12], Rinv[12];
+    double sig[16];          // [leg][2 (fx tied) + (fy tied)] = 1 / (Rz + [fx tied] mu^2 Rx + [fy tied] mu^2 Ry)
+};
+
+// shared memory of one robot
+struct Sh {
+    double E1[72];           // backward: (P Bbar) blocks [a][i][c]; forward: x (12) | mu partials (24) | wrench partials (24)
+    double E3[12];           // backward: q ; epilogue: co-state
+    double E4[78];           // backward: rows of (D A) and d of the threads p, rpy ; reductions
+    double cst[12];          // cy, sy, 1/m, Iinv[9]
+    double ring[2][24];      // inputs of a stage, prefetched: lever arms (12) | reference column (12)
+    int flag[8];
+};
+
+CMPC_HD size_t robot_bytes(int N) { return (sizeof(Sh) + (size_t)3 * 4 * N + 15) & ~(size_t)15; }
+CMPC_HD unsigned char* codes_of(Sh* sh) { return reinterpret_cast<unsigned char*>(sh) + sizeof(Sh); }
+
+// per-thread state that lives across synchronisation points
+struct TS {
+    double P[36];            // block row a of P, P[i*12 + c]
+    double pv[3];            // block a of p ; forward: block a of x
+    double lam[21];          // Lam_k, lower triangle
+    double wh[6];            // what_k
+    double qa[3];            // q_a, then d_a
+    double ax[3];            // forward: block a of A x_k
+    double red[4];           // epilogue partial reductions
+    int chg, cyc;
+};
+
+CMPC_HD int lt(int i, int j) { return ((i * (i + 1)) >> 1) + j; }      // lower-triangle index, i >= j
+
+CMPC_HD double wr_rsqrt(double v) {
+#if defined(__CUDA_ARCH__)
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(v));
+    const double tt = y0 * y0;
+    const double e = fma(-tt, v, 1.0);
+    const double pl = fma(e, 0.375, 0.5);
+    const double u = y0 * e;
+    return fma(pl, u, y0);
+#else
+    return 1.0 / sqrt(v);
+#endif
+}
+
+// ---- asynchronous copies of 8 bytes global -> shared (device: cp.async; host: plain copy)
+CMPC_HD void cp8(double* dst_smem, const double* src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#else
+    *dst_smem = *src;
+#endif
+}
+CMPC_HD void cp_commit_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// foot projection for a working-set code: bit 0 fz pinned at fz_min, bits 1-2 fx (0 free, 1 = +mu fz, 2 = -mu fz),
+// bits 3-4 fy likewise; SWING = not in stance
+struct FootP { double dx, dy, sg, zx, zy, fh; };
+CMPC_HD FootP foot_proj(unsigned char code, int leg, const Tab& tb, double mu, double fz_min) {
+    const bool st = code != SWING;
+    const int c = st ? (int)code : 0;
+    const int az = c & 1, ax = (c >> 1) & 3, ay = (c >> 3) & 3;
+    FootP f;
+    f.zx = ax == 0 ? 0.0 : (ax == 1 ? mu : -mu);
+    f.zy = ay == 0 ? 0.0 : (ay == 1 ? mu : -mu);
+    f.dx = (st && ax == 0) ? tb.Rinv[3 * leg] : 0.0;
+    f.dy = (st && ay == 0) ? tb.Rinv[3 * leg + 1] : 0.0;
+    f.sg = (st && !az) ? tb.sig[leg * 4 + (ax != 0 ? 2 : 0) + (ay != 0 ? 1 : 0)] : 0.0;
+    f.fh = (st && az) ? fz_min : 0.0;
+    return f;
+}
+
+// W = Iinv [r]x   (row-major 3 x 3)
+CMPC_HD void foot_W(const double* Ii, const double* r, double* W) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        W[i * 3 + 0] = Ii[i * 3 + 1] * r[2] - Ii[i * 3 + 2] * r[1];
+        W[i * 3 + 1] = -Ii[i * 3 + 0] * r[2] + Ii[i * 3 + 2] * r[0];
+        W[i * 3 + 2] = Ii[i * 3 + 0] * r[1] - Ii[i * 3 + 1] * r[0];
+    }
+}
+
+// in-place Cholesky of a 6 x 6 lower triangle; di = reciprocal diagonal.  Returns the smallest pivot.
+CMPC_HD double chol6(double* G, double* di) {
+    double pmin = 1e300;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double s = G[lt(j, j)];
+#pragma unroll
+        for (int m = 0; m < j; ++m) s -= G[lt(j, m)] * G[lt(j, m)];
+        pmin = fmin(pmin, s);
+        const double r = wr_rsqrt(s);
+        di[j] = r;
+        G[lt(j, j)] = s * r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = G[lt(i, j)];
+#pragma unroll
+            for (int m = 0; m < j; ++m) v -= G[lt(i, m)] * G[lt(j, m)];
+            G[lt(i, j)] = v * r;
+        }
+    }
+    return pmin;
+}
+// y <- L^-1 y
+CMPC_HD void fsub6(const double* L, const double* di, double* y) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double s = y[j];
+#pragma unroll
+        for (int m = 0; m < j; ++m) s -= L[lt(j, m)] * y[m];
+        y[j] = s * di[j];
+    }
+}
+// y <- L^-T y
+CMPC_HD void bsub6(const double* L, const double* di, double* y) {
+#pragma unroll
+    for (int j = 5; j >= 0; --j) {
+        double s = y[j];
+#pragma unroll
+        for (int m = j + 1; m < 6; ++m) s -= L[lt(m, j)] * y[m];
+        y[j] = s * di[j];
+    }
+}
+// out = L w
+CMPC_HD void lmul6(const double* L, const double* w, double* out) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m <= j; ++m) s += L[lt(j, m)] * w[m];
+        out[j] = s;
+    }
+}
+
+struct Env {                 // what one quad needs to know about its robot (uniform inside the quad)
+    const Params* p;
+    const Tab* tb;
+    QpIn in;
+    QpOut o;
+    D2* gains;               // this thread's slots: gains[(k * GAIN_D2 + e) * gstride]
+    size_t gstride;
+    double dt, h;
+};
+
+// block a of  Bbar w
+CMPC_HD void bbar_rows(int a, const double* cst, double dt, double h, const double* w, double* out) {
+    const double cy = cst[0], sy = cst[1], minv = cst[2];
+    const double cf = (a == 0) ? h * minv : (a == 1 ? h : (a == 2 ? dt * minv : dt));
+    const bool tq = (a & 1) != 0;         // selects, not pointer arithmetic: w is a register array
+    const double s0 = tq ? w[3] : w[0], s1 = tq ? w[4] : w[1], s2 = tq ? w[5] : w[2];
+    const double c = (a == 1) ? cy : 1.0, sn = (a == 1) ? sy : 0.0;
+    out[0] = cf * (c * s0 + sn * s1);
+    out[1] = cf * (-sn * s0 + c * s1);
+    out[2] = cf * s2;
+}
+
+// prefetch the inputs of a stage: lever arms of step kr, reference column kx (clamped by the caller)
+CMPC_HD void ring_issue(int q, Sh* sh, int slot, const QpIn& in, int kr, int kx) {
+    const int N = in.N;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        cp8(&sh->ring[slot][3 * q + c], in.r_foot + (size_t)(3 * q + c) * N + kr);
+        cp8(&sh->ring[slot][12 + 3 * q + c], in.x_ref + (size_t)(3 * q + c) * N + kx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// robot set-up: constants, initial working set (from the contact table, or from the previous duals when warm)
+// ------------------------------------------------------------------------------------------------------------------
+CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int warm) {
+    const int N = e.in.N;
+    unsigned char* codes = codes_of(sh);
+    int nst = 0;
+    WR_Q_BEGIN
+    (void)t; (void)q;
+    if (valid) {
+        if (q == 0) {
+            DynCommon dc;
+            dyn_common(dc, e.in.x_ref, N, e.in.I_world, e.in.mass, e.in.dt);
+            sh->cst[0] = dc.cy; sh->cst[1] = dc.sy; sh->cst[2] = dc.minv;
+            for (int i = 0; i < 9; ++i) sh->cst[3 + i] = dc.Iinv[i];
+        }
+        for (int k = 0; k < N; ++k) {
+            const int st = mask_bit(e.in.mask, N, q, k);
+            unsigned char c = SWING;
+            if (st) {
+                c = 0;
+                if (warm) {
+                    const double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
+                    const int az = e.o.y[12 * k + 3 * q + 2] < 0.0;
+                    const int ax = yf[0] > 0.0 ? 1 : (yf[1] > 0.0 ? 2 : 0);
+                    const int ay = yf[2] > 0.0 ? 1 : (yf[3] > 0.0 ? 2 : 0);
+                    c = (unsigned char)(az | (ax << 1) | (ay << 3));
+                }
+            }
+            codes[4 * k + q] = c;
+            codes[4 * N + 4 * k + q] = 254;          // "previous" sets that match nothing
+            codes[8 * N + 4 * k + q] = 254;
+        }
+    }
+    WR_Q_END
+    WR_SYNC();
+    if (valid) for (int i = 0; i < 4 * N; ++i) nst += codes[i] != SWING;      // uniform in the quad
+    return nst;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward sweep for the working set cur.  Returns the smallest pivot seen (<= 0: not positive definite).
+// ------------------------------------------------------------------------------------------------------------------
+CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const unsigned char* cur) {
+    const int N = e.in.N;
+    const Params& p = *e.p;
+    const Tab& tb = *e.tb;
+    const double dt = e.dt, h = e.h;
+    double pmin = 1e300;
+    // terminal cost and the first prefetch
+    WR_Q_BEGIN
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) t.P[i * 12 + c] = (c == 3 * q + i) ? tb.Q[3 * q + i] : 0.0;
+        t.pv[i] = -tb.Q[3 * q + i] * e.in.x_ref[(size_t)(3 * q + i) * N + (N - 1)];
+    }
+    ring_issue(q, sh, (N - 1) & 1, e.in, N - 1, N >= 2 ? N - 2 : 0);
+    WR_Q_END
+    for (int k = N - 1; k >= 0; --k) {
+        const double* ring = sh->ring[k & 1];
+        WR_Q_BEGIN
+        (void)t;
+        cp_commit_wait();
+        WR_Q_END
+        WR_SYNC();
+        // ---- phase 1: Lam_k, what_k (every thread, all four feet), own rows of P Bbar, q_a
+        WR_Q_BEGIN
+        if (k > 0) ring_issue(q, sh, (k - 1) & 1, e.in, k - 1, k >= 2 ? k - 2 : 0);
+        const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
+#pragma unroll
+        for (int i = 0; i < 21; ++i) t.lam[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t.wh[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const FootP f = foot_proj(cur[4 * k + j], j, tb, p.mu, p.fz_min);
+            double W[9], Wz[3];
+            foot_W(sh->cst + 3, ring + 3 * j, W);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) Wz[m] = W[m * 3] * f.zx + W[m * 3 + 1] * f.zy + W[m * 3 + 2];
+            const double sx = f.sg * f.zx, sy_ = f.sg * f.zy;
+            t.lam[lt(0, 0)] += f.dx + sx * f.zx;
+            t.lam[lt(1, 0)] += sx * f.zy;
+            t.lam[lt(1, 1)] += f.dy + sy_ * f.zy;
+            t.lam[lt(2, 0)] += sx;
+            t.lam[lt(2, 1)] += sy_;
+            t.lam[lt(2, 2)] += f.sg;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                t.lam[lt(3 + m, 0)] += f.dx * W[m * 3] + sx * Wz[m];
+                t.lam[lt(3 + m, 1)] += f.dy * W[m * 3 + 1] + sy_ * Wz[m];
+                t.lam[lt(3 + m, 2)] += f.sg * Wz[m];
+                const double a0 = f.dx * W[m * 3], a1 = f.dy * W[m * 3 + 1], a2 = f.sg * Wz[m];
+#pragma unroll
+                for (int n = 0; n <= m; ++n) t.lam[lt(3 + m, 3 + n)] += a0 * W[n * 3] + a1 * W[n * 3 + 1] + a2 * Wz[n];
+            }
+            t.wh[0] += f.fh * f.zx; t.wh[1] += f.fh * f.zy; t.wh[2] += f.fh;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) t.wh[3 + m] += f.fh * Wz[m];
+        }
+        // ghat = g + Bbar what
+        double gh[12];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, t.wh, gh + 3 * a);
+        gh[2] += -9.81 * h;
+        gh[8] += -9.81 * dt;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double* Pi = t.P + i * 12;
+            double* o = sh->E1 + q * 18 + i * 6;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = minv * (h * Pi[c] + dt * Pi[6 + c]);
+            o[3] = h * (Pi[3] * cy - Pi[4] * sy) + dt * Pi[9];
+            o[4] = h * (Pi[3] * sy + Pi[4] * cy) + dt * Pi[10];
+            o[5] = h * Pi[5] + dt * Pi[11];
+            double s = t.pv[i];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) s += Pi[c] * gh[c];
+            t.qa[i] = s;
+            sh->E3[3 * q + i] = s;
+        }
+        WR_Q_END
+        WR_SYNC();
+        // ---- phase 2: 6 x 6 factorizations (every thread), gains, own rows of D = P - (P Bbar) Phi (P Bbar)', D A
+        WR_Q_BEGIN
+        const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
+        const double* E1 = sh->E1;
+        double L[21], di[6];
+        {   // Gbar = Bbar' (P Bbar), lower triangle
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) L[lt(r, c)] = minv * (h * E1[0 * 18 + r * 6 + c] + dt * E1[2 * 18 + r * 6 + c]);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double x0 = E1[18 + c], x1 = E1[18 + 6 + c], x2 = E1[18 + 12 + c];
+                const double r0 = h * (cy * x0 - sy * x1) + dt * E1[54 + c];
+                const double r1 = h * (sy * x0 + cy * x1) + dt * E1[54 + 6 + c];
+                const double r2 = h * x2 + dt * E1[54 + 12 + c];
+                if (c <= 3) L[lt(3, c)] = r0;
+                if (c <= 4) L[lt(4, c)] = r1;
+                L[lt(5, c)] = r2;
+            }
+        }
+        pmin = fmin(pmin, chol6(L, di));
+        double Ln[21], dn[6];
+        {   // Nn = I + L' Lam L, column by column
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double tj[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = j; m < 6; ++m) s += t.lam[r >= m ? lt(r, m) : lt(m, r)] * L[lt(m, j)];
+                    tj[r] = s;
+                }
+#pragma unroll
+                for (int i = j; i < 6; ++i) {
+                    double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int m = i; m < 6; ++m) s += L[lt(m, i)] * tj[m];
+                    Ln[lt(i, j)] = s;
+                }
+            }
+        }
+        chol6(Ln, dn);
+        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        // vector part: bq = Bbar' q, kbar = Gam bq, phiq = Phi bq
+        double phiq[6];
+        {
+            const double* qv = sh->E3;
+            double y[6], w[6], kb[6];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) y[c] = minv * (h * qv[c] + dt * qv[6 + c]);
+            y[3] = h * (cy * qv[3] - sy * qv[4]) + dt * qv[9];
+            y[4] = h * (sy * qv[3] + cy * qv[4]) + dt * qv[10];
+            y[5] = h * qv[5] + dt * qv[11];
+            fsub6(L, di, y);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) w[c] = y[c];
+            fsub6(Ln, dn, w);
+            bsub6(Ln, dn, w);
+            lmul6(L, w, kb);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) phiq[c] = y[c] - w[c];
+            bsub6(L, di, phiq);
+            D2 kk;
+            kk.x = q == 0 ? kb[0] : (q == 1 ? kb[2] : (q == 2 ? kb[4] : 0.0));
+            kk.y = q == 0 ? kb[1] : (q == 1 ? kb[3] : (q == 2 ? kb[5] : 0.0));
+            g[9 * e.gstride] = kk;
+        }
+        const double* own = E1 + q * 18;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double y[6], w[6], kt[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) y[c] = own[i * 6 + c];
+            fsub6(L, di, y);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) w[c] = y[c];
+            fsub6(Ln, dn, w);
+            bsub6(Ln, dn, w);
+            lmul6(L, w, kt);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { D2 v; v.x = kt[2 * c]; v.y = kt[2 * c + 1]; g[(3 * i + c) * e.gstride] = v; }
+            if (k > 0) {
+                double z[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) z[c] = y[c] - w[c];
+                bsub6(L, di, z);
+                double* Pi = t.P + i * 12;
+#pragma unroll
+                for (int b = 0; b < 12; ++b) {
+                    double s = Pi[b];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s -= z[c] * E1[b * 6 + c];
+                    Pi[b] = s;
+                }
+                double d = t.qa[i];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d -= own[i * 6 + c] * phiq[c];
+                t.qa[i] = d;
+                // D A (own row)
+                Pi[6] += dt * Pi[0]; Pi[7] += dt * Pi[1]; Pi[8] += dt * Pi[2];
+                Pi[9] += dt * (cy * Pi[3] - sy * Pi[4]);
+                Pi[10] += dt * (sy * Pi[3] + cy * Pi[4]);
+                Pi[11] += dt * Pi[5];
+                if (q < 2) {
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) sh->E4[q * 39 + i * 12 + c] = Pi[c];
+                    sh->E4[q * 39 + 36 + i] = d;
+                }
+            }
+        }
+        WR_Q_END
+        if (k == 0) break;
+        WR_SYNC();
+        // ---- phase 3: P <- Q + A'(D A),  p <- -Q xref + A' d
+        WR_Q_BEGIN
+        const double dtc = q >= 2 ? dt : 0.0;
+        const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
+        const double* X = sh->E4 + (q & 1) * 39;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const double x0 = X[c], x1 = X[12 + c], x2 = X[24 + c];
+            t.P[c] += dtc * (rc * x0 - rs * x1);
+            t.P[12 + c] += dtc * (rs * x0 + rc * x1);
+            t.P[24 + c] += dtc * x2;
+        }
+        const double d0 = X[36], d1 = X[37], d2 = X[38];
+        const double a0 = t.qa[0] + dtc * (rc * d0 - rs * d1), a1 = t.qa[1] + dtc * (rs * d0 + rc * d1), a2 = t.qa[2] + dtc * d2;
+        const double q0 = tb.Q[3 * q], q1 = tb.Q[3 * q + 1], q2 = tb.Q[3 * q + 2];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {       // selects: P is a register array, its indices must be compile-time constants
+            t.P[c] += (c == 3 * q) ? q0 : 0.0;
+            t.P[12 + c] += (c == 3 * q + 1) ? q1 : 0.0;
+            t.P[24 + c] += (c == 3 * q + 2) ? q2 : 0.0;
+        }
+        t.pv[0] = a0 - q0 * ring[12 + 3 * q + 0];
+        t.pv[1] = a1 - q1 * ring[12 + 3 * q + 1];
+        t.pv[2] = a2 - q2 * ring[12 + 3 * q + 2];
+        WR_Q_END
+    }
+    WR_SYNC();
+    return pmin;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward sweep: states, forces, multipliers, next working set.  Writes forces / stance duals to o.u / o.y when
+// `valid`.  Returns bit 0: the working set changed, bit 1: the new set equals `prev` (a 2-cycle).
+// ------------------------------------------------------------------------------------------------------------------
+CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur,
+                          const unsigned char* prev, unsigned char* next) {
+    const int N = e.in.N;
+    const Params& p = *e.p;
+    const Tab& tb = *e.tb;
+    const double dt = e.dt, h = e.h;
+    const double tol = 1e-10;
+    double* xs = sh->E1;
+    double* mup = sh->E1 + 12;
+    double* wp = sh->E1 + 36;
+    WR_Q_BEGIN
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t.pv[i] = e.in.x0[3 * q + i];
+    t.chg = 0; t.cyc = 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cp8(&sh->ring[0][3 * q + c], e.in.r_foot + (size_t)(3 * q + c) * N);
+    WR_Q_END
+    for (int k = 0; k < N; ++k) {
+        double* ring = sh->ring[k & 1];
+        // ---- F1: publish x
+        WR_Q_BEGIN
+        cp_commit_wait();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xs[3 * q + i] = t.pv[i];
+        WR_Q_END
+        WR_SYNC();
+        // ---- F2: A x (own block), partial wrench co-state
+        WR_Q_BEGIN
+        if (k + 1 < N) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cp8(&sh->ring[(k + 1) & 1][3 * q + c], e.in.r_foot + (size_t)(3 * q + c) * N + k + 1);
+        }
+        const D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        const double dtf = q < 2 ? dt : 0.0;
+        const double rc = q == 1 ? sh->cst[0] : 1.0, rs = q == 1 ? sh->cst[1] : 0.0;
+        const double* X = xs + 3 * (q | 2);
+        t.ax[0] = t.pv[0] + dtf * (rc * X[0] + rs * X[1]);
+        t.ax[1] = t.pv[1] + dtf * (-rs * X[0] + rc * X[1]);
+        t.ax[2] = t.pv[2] + dtf * X[2];
+        const D2 kk = g[9 * e.gstride];
+        double mp[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mp[2 * c] = (q == c) ? kk.x : 0.0; mp[2 * c + 1] = (q == c) ? kk.y : 0.0; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const D2 v = g[(3 * i + c) * e.gstride];
+                mp[2 * c] += v.x * t.ax[i];
+                mp[2 * c + 1] += v.y * t.ax[i];
+            }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) mup[q * 6 + c] = mp[c];
+        WR_Q_END
+        WR_SYNC();
+        // ---- F3: foot q -- force, multipliers, next code, wrench contribution
+        WR_Q_BEGIN
+        double mu6[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) mu6[c] = mup[c] + mup[6 + c] + mup[12 + c] + mup[18 + c];
+        const unsigned char code = cur[4 * k + q];
+        const FootP f = foot_proj(code, q, tb, p.mu, p.fz_min);
+        double W[9];
+        foot_W(sh->cst + 3, ring + 3 * q, W);
+        double tv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tv[c] = mu6[c] + W[c] * mu6[3] + W[3 + c] * mu6[4] + W[6 + c] * mu6[5];
+        const double zt = f.zx * tv[0] + f.zy * tv[1] + tv[2];
+        double fo[3];
+        fo[0] = f.fh * f.zx - f.dx * tv[0] - f.sg * f.zx * zt;
+        fo[1] = f.fh * f.zy - f.dy * tv[1] - f.sg * f.zy * zt;
+        fo[2] = f.fh - f.sg * zt;
+        unsigned char nc = SWING;
+        double l5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (code != SWING) {
+            const int az = code & 1, ax = (code >> 1) & 3, ay = (code >> 3) & 3;
+            const double d0 = tb.R[3 * q] * fo[0] + tv[0], d1 = tb.R[3 * q + 1] * fo[1] + tv[1], d2 = tb.R[3 * q + 2] * fo[2] + tv[2];
+            double lx = 0.0, ly = 0.0;
+            if (ax == 1) { lx = -2.0 * d0; l5[1] = lx; } else if (ax == 2) { lx = 2.0 * d0; l5[2] = lx; }
+            if (ay == 1) { ly = -2.0 * d1; l5[3] = ly; } else if (ay == 2) { ly = 2.0 * d1; l5[4] = ly; }
+            if (az) l5[0] = 2.0 * d2 - p.mu * (lx + ly);
+            const double s0 = l5[0] + (p.fz_min - fo[2]);
+            const double s1 = l5[1] + (fo[0] - p.mu * fo[2]), s2 = l5[2] + (-fo[0] - p.mu * fo[2]);
+            const double s3 = l5[3] + (fo[1] - p.mu * fo[2]), s4 = l5[4] + (-fo[1] - p.mu * fo[2]);
+            const int nz = s0 > tol;
+            const int nx = (s1 > tol && s1 >= s2) ? 1 : ((s2 > tol && s2 > s1) ? 2 : 0);
+            const int ny = (s3 > tol && s3 >= s4) ? 1 : ((s4 > tol && s4 > s3) ? 2 : 0);
+            nc = (unsigned char)(nz | (nx << 1) | (ny << 3));
+        }
+        next[4 * k + q] = nc;
+        t.chg |= (nc != code);
+        t.cyc &= (nc == prev[4 * k + q]);
+        if (valid) {
+            double* uo = e.o.u + 12 * k + 3 * q;
+            uo[0] = fo[0]; uo[1] = fo[1]; uo[2] = fo[2];
+            if (code != SWING) e.o.y[12 * k + 3 * q + 2] = -l5[0];
+            double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
+            yf[0] = l5[1]; yf[1] = l5[2]; yf[2] = l5[3]; yf[3] = l5[4];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            wp[q * 6 + c] = fo[c];
+            wp[q * 6 + 3 + c] = W[c * 3] * fo[0] + W[c * 3 + 1] * fo[1] + W[c * 3 + 2] * fo[2];
+        }
+        WR_Q_END
+        WR_SYNC();
+        // ---- F4: x_{k+1}
+        WR_Q_BEGIN
+        double w6[6], bw[3];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) w6[c] = wp[c] + wp[6 + c] + wp[12 + c] + wp[18 + c];
+        bbar_rows(q, sh->cst, dt, h, w6, bw);
+        t.pv[0] = t.ax[0] + bw[0];
+        t.pv[1] = t.ax[1] + bw[1];
+        t.pv[2] = t.ax[2] + bw[2] + (q == 0 ? -9.81 * h : (q == 2 ? -9.81 * dt : 0.0));
+        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        D2 a; a.x = t.pv[0]; a.y = t.pv[1];
+        D2 b; b.x = t.pv[2]; b.y = 0.0;
+        g[10 * e.gstride] = a;
+        g[11 * e.gstride] = b;
+        WR_Q_END
+    }
+    WR_SYNC();
+    int res = 0;
+    WR_Q_BEGIN
+    sh->flag[q] = t.chg | (t.cyc << 1);
+    WR_Q_END
+    WR_SYNC();
+    res = (sh->flag[0] | sh->flag[1] | sh->flag[2] | sh->flag[3]) & 1;
+    res |= (sh->flag[0] & sh->flag[1] & sh->flag[2] & sh->flag[3]) & 2;
+    WR_SYNC();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// epilogue of a robot whose working set has settled: co-states, stationarity and feasibility from first principles
+// (independent of the factorizations), the remaining outputs in the reference's layouts.  Returns 1 if accepted.
+// ------------------------------------------------------------------------------------------------------------------
+CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur, int nst, int sweeps,
+                     int warm) {
+    const int N = e.in.N;
+    const Params& p = *e.p;
+    const Tab& tb = *e.tb;
+    const double dt = e.dt, h = e.h;
+    double* nus = sh->E3;
+    WR_Q_BEGIN
+    t.red[0] = 0.0; t.red[1] = 0.0; t.red[2] = 0.0; t.red[3] = 0.0;       // rd, rp, objective part, active rows
+    t.ax[0] = 0.0; t.ax[1] = 0.0; t.ax[2] = 0.0;                          // co-state block
+    WR_Q_END
+    for (int k = N - 1; k >= 0; --k) {
+        WR_Q_BEGIN
+        const D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        const D2 a = g[10 * e.gstride], b = g[11 * e.gstride];
+        const double xk[3] = {a.x, a.y, b.x};
+        const double dtc = (q >= 2 && k < N - 1) ? dt : 0.0;
+        const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
+        const double* X = nus + 3 * (q & 1);
+        double s[3];
+        s[0] = dtc * (rc * X[0] - rs * X[1]);
+        s[1] = dtc * (rs * X[0] + rc * X[1]);
+        s[2] = dtc * X[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double xr = valid ? e.in.x_ref[(size_t)(3 * q + i) * N + k] : 0.0;
+            const double dd = xk[i] - xr;
+            s[i] += (k < N - 1 ? t.ax[i] : 0.0) - 2.0 * tb.Q[3 * q + i] * dd;
+            t.red[2] += tb.Q[3 * q + i] * (dd * dd - xr * xr);
+            if (valid && e.o.X) e.o.X[12 * k + 3 * q + i] = xk[i];
+        }
+        t.qa[0] = s[0]; t.qa[1] = s[1]; t.qa[2] = s[2];
+        WR_Q_END
+        WR_SYNC();            // everybody has read the co-state of step k+1
+        WR_Q_BEGIN
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            t.ax[i] = t.qa[i];
+            nus[3 * q + i] = t.qa[i];
+            if (valid && e.o.nu) e.o.nu[12 * k + 3 * q + i] = t.qa[i];
+        }
+        WR_Q_END
+        WR_SYNC();
+        WR_Q_BEGIN
+        const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
+        double bn[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bn[c] = minv * (h * nus[c] + dt * nus[6 + c]);
+        bn[3] = h * (cy * nus[3] - sy * nus[4]) + dt * nus[9];
+        bn[4] = h * (sy * nus[3] + cy * nus[4]) + dt * nus[10];
+        bn[5] = h * nus[5] + dt * nus[11];
+        if (valid) {
+            double r[3], W[9], s3[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r[c] = e.in.r_foot[(size_t)(3 * q + c) * N + k];
+            foot_W(sh->cst + 3, r, W);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s3[c] = bn[c] + W[c] * bn[3] + W[3 + c] * bn[4] + W[6 + c] * bn[5];
+            if (cur[4 * k + q] != SWING) {
+                const double* f = e.o.u + 12 * k + 3 * q;
+                const double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
+                const double l0 = -e.o.y[12 * k + 3 * q + 2];
+                const double atl[3] = {yf[0] - yf[1], yf[2] - yf[3], -l0 - p.mu * (yf[0] + yf[1] + yf[2] + yf[3])};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    t.red[0] = fmax(t.red[0], fabs(2.0 * tb.R[3 * q + c] * f[c] - s3[c] + atl[c]));
+                    t.red[2] += tb.R[3 * q + c] * f[c] * f[c];
+                }
+                const double v = fmax(p.fz_min - f[2], fmax(fabs(f[0]), fabs(f[1])) - p.mu * f[2]);
+                t.red[1] = fmax(t.red[1], v);
+                t.red[3] += (l0 > 0.0) + (yf[0] > 0.0) + (yf[1] > 0.0) + (yf[2] > 0.0) + (yf[3] > 0.0);
+                // multipliers must not be negative (they are > 0 on the working set by construction)
+                t.red[0] = fmax(t.red[0], fmax(fmax(-l0, -yf[0]), fmax(fmax(-yf[1], -yf[2]), -yf[3])));
+                e.o.y[12 * k + 3 * q] = 0.0;
+                e.o.y[12 * k + 3 * q + 1] = 0.0;
+            } else {
+                e.o.y[12 * k + 3 * q] = s3[0];
+                e.o.y[12 * k + 3 * q + 1] = s3[1];
+                e.o.y[12 * k + 3 * q + 2] = s3[2];
+            }
+        }
+        WR_Q_END
+        WR_SYNC();
+    }
+    WR_Q_BEGIN
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sh->E4[4 * q + i] = t.red[i];
+    WR_Q_END
+    WR_SYNC();
+    const double* R4 = sh->E4;
+    const double rd = fmax(fmax(R4[0], R4[4]), fmax(R4[8], R4[12]));
+    const double rp = fmax(fmax(R4[1], R4[5]), fmax(R4[9], R4[13]));
+    const double obj = R4[2] + R4[6] + R4[10] + R4[14];
+    const double na = R4[3] + R4[7] + R4[11] + R4[15];
+    const int ok = (rd <= 1e-6) && (rp <= 1e-9);
+    WR_Q_BEGIN
+    (void)t;
+    if (valid && ok && q == 0) {
+        const double rho = (warm && e.o.rho && *e.o.rho > 0.0) ? *e.o.rho : p.rho0;
+        if (e.o.rho) *e.o.rho = rho;
+        *e.o.status = ST_SOLVED;
+        *e.o.iters = 0;
+        e.o.stats[0] = fmax(rp, 0.0);
+        e.o.stats[1] = rd;
+        e.o.stats[2] = obj;
+        e.o.stats[3] = (double)(3 * nst);
+        e.o.stats[4] = na;
+        e.o.stats[5] = rho;
+        e.o.stats[6] = (double)(sweeps - 1);
+        e.o.stats[7] = (double)(sweeps > 1 ? (int)PATH_WRENCH : (int)PATH_RICCATI);
+    }
+    WR_Q_END
+    WR_SYNC();
+    return ok;
+}
+
+// One robot from set-up to outputs (host emulation; the device kernel in cmpc.cu interleaves these steps over the
+// eight robots of a warp).  Returns 1 if finished here, 0 if the robot goes on to the condensed kernel.
+CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int warm, int* sweeps_out) {
+    const int N = e.in.N;
+    unsigned char* codes = codes_of(sh);
+    const int nst = init_robot(qlane, true, ts, sh, e, warm);
+    if (sweeps_out) *sweeps_out = 0;
+    if (nst == 0 || nst > nfmax) return 0;
+    const int max_it = e.p->pdas_max_iter;
+    for (int it = 0; it < max_it; ++it) {
+        const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
+        unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
+        const unsigned char* prev = codes + (size_t)((it + 2) % 3) * 4 * N;
+        const double pmin = backward_sweep(qlane, ts, sh, e, cur);
+        if (!(pmin > 0.0)) return 0;
+        const int fl = forward_sweep(qlane, true, ts, sh, e, cur, prev, next);
+        if (sweeps_out) *sweeps_out = it + 1;
+        if (!(fl & 1)) return epilogue(qlane, true, ts, sh, e, cur, nst, it + 1, warm);
+        if (fl & 2) return 0;           // the new set is the one before: a 2-cycle
+    }
+    return 0;
+}
+
+CMPC_HD void fill_tab(Tab& tb, const Params& p, int i) {
+    // entry i of the tables (i < 12: Q, R, Rinv; i < 16: sig)
+    if (i < 12) { tb.Q[i] = p.Q[i]; tb.R[i] = p.R[i]; tb.Rinv[i] = 1.0 / p.R[i]; }
+    if (i < 16) {
+        const int leg = i >> 2, tx = (i >> 1) & 1, ty = i & 1;
+        tb.sig[i] = 1.0 / (p.R[3 * leg + 2] + (tx ? p.mu * p.mu * p.R[3 * leg] : 0.0) + (ty ? p.mu * p.mu * p.R[3 * leg + 1] : 0.0));
+    }
+}
+
+}  // namespace wr
+}  // namespace cmpc

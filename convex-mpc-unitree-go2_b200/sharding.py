@@ -8,7 +8,7 @@ import numpy as np
 
 STAT_FIELDS = ("qps_count", "elapsed_ms", "solved", "max_iter", "inaccurate", "failed",
                "path_unconstrained", "path_active_set", "path_admm", "path_admm_polish",
-               "as_iters_sum", "admm_iters_sum", "n_free_sum", "r_prim_max", "r_dual_max", "flops", "path_riccati", "flops_route")
+               "as_iters_sum", "admm_iters_sum", "n_free_sum", "r_prim_max", "r_dual_max", "flops", "path_riccati", "flops_route", "path_wrench_as")
 
 
 def env_rank_world():
@@ -46,6 +46,7 @@ def local_stats(status, iters, stats, elapsed_ms, flops=0.0, flops_route=0.0):
     rec[15] = flops
     rec[16] = (path == 4).sum()          # finished by the Riccati pre-pass (no active constraint)
     rec[17] = flops_route
+    rec[18] = (path == 5).sum()          # active set settled by Riccati sweeps (wrench-space PDAS kernel)
     return rec
 
 

@@ -51,7 +51,7 @@ typedef struct cmpc_handle cmpc_handle;
 #define CMPC_STAT_NACT    4   /* active inequality rows at the solution       */
 #define CMPC_STAT_RHO     5   /* final ADMM rho                               */
 #define CMPC_STAT_ASITERS 6   /* active-set iterations                        */
-#define CMPC_STAT_PATH    7   /* 0 unconstrained, 1 active-set, 2 ADMM, 3 ADMM+polish, 4 unconstrained via the Riccati pre-pass */
+#define CMPC_STAT_PATH    7   /* 0 unconstrained, 1 active-set, 2 ADMM, 3 ADMM+polish, 4 unconstrained via a Riccati sweep, 5 active set via Riccati sweeps (pre-pass 4) */
 
 /* Replaces CentroidalMPC.__init__ (centroidal_mpc.py:41-67): allocates nothing on the device but
  * fixes the horizon N (16, 32 or 48 ...; <= 48) and the largest batch the handle will see.     */
@@ -75,16 +75,28 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax);
  * two implementations can be compared on the same inputs.                                        */
 int cmpc_set_generic(cmpc_handle* h, int on);
 
-/* Nominal pre-pass (active-set mode with raw inputs): a Riccati sweep finishes every robot whose unconstrained
- * minimiser already satisfies the friction-pyramid and fz_min rows (nominal trot) and hands
- * the others to the condensed active-set kernel through a device work-list.  Same optimum either way.
+/* Pre-pass (active-set mode with raw inputs) ahead of the condensed active-set kernel; robots the pre-pass cannot
+ * finish reach that kernel through a device work-list.  Same optimum either way.
  *   0  off: every robot through the condensed kernel
- *   1  reference sweep, one robot per warp (cmpc_riccati.cuh; the version the host emulation tests)
- *   2  register-resident sweep, two robots per warp (cmpc_riccati2.cuh)
- *   3  (default) = 2 with the sixteen robots of a CTA in lock-step, so that they share fetched instruction lines;
- *      falls back to 2 when sixteen robots do not fit shared memory (N > 16)
+ *   1  Riccati sweep, one robot per warp (cmpc_riccati.cuh): finishes robots whose unconstrained minimiser is feasible
+ *   2  the same, register-resident, two robots per warp (cmpc_riccati2.cuh)
+ *   3  = 2 with the sixteen robots of a CTA in lock-step (falls back to 2 when they do not fit shared memory, N > 16)
+ *   4  (default) wrench-space projected Riccati + primal-dual active set (cmpc_wrench.cuh), four threads per robot:
+ *      finishes constrained robots too (one Riccati sweep per working set, O(N) in the horizon); only robots whose
+ *      working set cycles go on to the condensed kernel
  * Batches below 2 048 robots skip the pre-pass (they are latency-bound; the extra launch only adds latency).  */
 int cmpc_set_prepass(cmpc_handle* h, int on);
+
+/* Workspace (section 8b "no allocation inside solve").  A handle keeps four SLOTS of device workspace (work-list,
+ * counters, gain scratch, L2-resident scratch of the condensed kernel); consecutive cmpc_solve / cmpc_build calls
+ * rotate over them, so AT MOST FOUR calls of one handle may be in flight at a time (on any streams), and calls on
+ * one handle must come from one host thread.  cmpc_reserve sizes the slots for batches of up to B robots with the
+ * current stance bound; after it, cmpc_solve allocates nothing and may be captured in a CUDA graph.  Without it the
+ * first cmpc_solve reserves for max_batch robots (device-synchronising; not during capture).  A later
+ * cmpc_set_max_stance or a larger batch re-reserves on the next call.  cmpc_workspace_bytes reports what
+ * cmpc_reserve(h, B) holds.                                                                                   */
+int cmpc_workspace_bytes(cmpc_handle* h, int B, size_t* bytes);
+int cmpc_reserve(cmpc_handle* h, int B);
 
 /* ComTraj.generate_traj (com_trajectory.py:27-211 with gait.py:21-24,40-74), batched: reference trajectory,
  * clamp of the world position target and lever arms CoM->foot over the horizon -- the producer of x_ref and

@@ -13,6 +13,7 @@
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_fast.cuh"
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_riccati.cuh"
 #include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_traj.cuh"
+#include "../../convex-mpc-unitree-go2_b200/csrc/cmpc_wrench.cuh"
 
 using namespace cmpc;
 
@@ -176,6 +177,40 @@ int emul_srb_step(int N, int B, const double* x, const double* u, const double* 
         traj::srb_step_one(N, x + (size_t)b * 12, u + (size_t)b * 12 * N, x_ref + (size_t)b * 12 * N, r_foot + (size_t)b * 12 * N,
                            I_world + (size_t)b * 9, mass[b], T, I_body, so, x_out + (size_t)b * 12, R_wb + (size_t)b * 9,
                            I_out + (size_t)b * 9, lever + (size_t)b * 12);
+    return 0;
+}
+
+// Wrench-space projected Riccati + PDAS (csrc/cmpc_wrench.cuh): the four threads of a quad run one after the other
+// between synchronisation points.  done[b] = 1 where the robot was finished here, sweeps[b] = Riccati sweeps used.
+int emul_wrench(const Params* p, int B, int N, int nfmax, const double* x0, const double* x_ref, const double* r_foot,
+                const double* I_world, const double* mass, double dt, const uint64_t* mask, int warm, double* u, double* y,
+                double* rho, double* X, double* nu, int32_t* status, int32_t* iters, double* stats, int32_t* done,
+                int32_t* sweeps) {
+    std::vector<unsigned char> buf(wr::robot_bytes(N) + 64);
+    wr::Sh* sh = reinterpret_cast<wr::Sh*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~(uintptr_t)15);
+    std::vector<wr::D2> gains((size_t)N * wr::GAIN_D2 * 4);
+    wr::Tab tb;
+    for (int i = 0; i < 16; ++i) wr::fill_tab(tb, *p, i);
+    wr::TS ts[4];
+    for (int b = 0; b < B; ++b) {
+        wr::Env e;
+        e.p = p; e.tb = &tb;
+        e.in = make_in(b, N, nullptr, nullptr, nullptr, x0, x_ref, r_foot, I_world, mass, dt, mask);
+        e.o.u = u + (size_t)b * 12 * N;
+        e.o.y = y + (size_t)b * 28 * N;
+        e.o.rho = rho ? rho + b : nullptr;
+        e.o.X = X ? X + (size_t)b * 12 * N : nullptr;
+        e.o.nu = nu ? nu + (size_t)b * 12 * N : nullptr;
+        e.o.status = status + b;
+        e.o.iters = iters + b;
+        e.o.stats = stats + (size_t)b * NSTAT;
+        e.gains = gains.data();      // thread q uses gains[... * 4 + q]: see the offset below
+        e.gstride = 4;
+        e.dt = dt; e.h = dt * dt / 2.0;
+        int sw = 0;
+        done[b] = wr::solve_robot(0, ts, sh, e, nfmax, warm, &sw);
+        sweeps[b] = sw;
+    }
     return 0;
 }
 

@@ -16,6 +16,7 @@ CORE = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_core.cuh"
 FAST = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_fast.cuh")
 RIC = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_riccati.cuh")
 TRAJ = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_traj.cuh")
+WRENCH = os.path.join(ROOT, "convex-mpc-unitree-go2_b200", "csrc", "cmpc_wrench.cuh")
 
 PHASE_OFFSET = np.array([0.5, 0.0, 0.0, 0.5])
 
@@ -50,7 +51,7 @@ def force_error(u, u_star):
 # ------------------------------------------------------------------------------------------------
 def build_emul():
     stale = (not os.path.exists(EMUL_LIB) or
-             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST), os.path.getmtime(RIC), os.path.getmtime(TRAJ)))
+             os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(EMUL_SRC), os.path.getmtime(CORE), os.path.getmtime(FAST), os.path.getmtime(RIC), os.path.getmtime(TRAJ), os.path.getmtime(WRENCH)))
     if stale:
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMUL_LIB, EMUL_SRC],
                        check=True)
@@ -154,6 +155,25 @@ class Emul:
                               _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
                               _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats), _p(done))
         return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask, done=done)
+
+    def wrench(self, rec, mask=None, nfmax=None, warm=0, state=None, **kw):
+        """Wrench-space projected Riccati + PDAS (csrc/cmpc_wrench.cuh); ``done`` marks the robots it finished,
+        ``sweeps`` the Riccati sweeps it ran."""
+        B, N = rec.B, rec.N
+        nfmax = 4 * N if nfmax is None else nfmax
+        if mask is None:
+            mask = self.contact_table(rec.t0, rec.dt, N, rec.gait_hz, rec.duty)
+        if state is None:
+            u = np.zeros((B, 12 * N)); y = np.zeros((B, 28 * N)); rho = np.zeros(B)
+        else:
+            u, y, rho = state
+        X = np.zeros((B, 12 * N)); nu = np.zeros((B, 12 * N))
+        st = np.zeros(B, np.int32); it = np.zeros(B, np.int32); stats = np.zeros((B, 8))
+        done = np.zeros(B, np.int32); sweeps = np.zeros(B, np.int32)
+        self.lib.emul_wrench(self.params(**kw), B, N, nfmax, _p(rec.x0), _p(rec.x_ref), _p(rec.r_foot),
+                             _p(rec.I_world), _p(rec.mass), ctypes.c_double(rec.dt), _p(mask), warm,
+                             _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats), _p(done), _p(sweeps))
+        return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask, done=done, sweeps=sweeps)
 
     def generate_traj(self, N, x0, R_wb, lever, cmd, t0, dt, hz, duty, hip, pos_des, off=PHASE_OFFSET):
         """csrc/cmpc_traj.cuh under the host emulation: returns (pos_des_out, x_ref (B,12,N), r_foot (B,4,3,N))."""
