@@ -1,5 +1,6 @@
 """Compile the CUDA library in-tree for sm_100a (B200).  No JIT cache, no torch extension machinery:
 one nvcc command, the resulting ``libcmpc.so`` sits next to this file and travels with the repo."""
+import hashlib
 import os
 import shutil
 import subprocess
@@ -22,11 +23,27 @@ def find_nvcc():
     raise RuntimeError("nvcc not found: the CUDA toolkit is required to build libcmpc.so")
 
 
+STAMP = os.path.join(HERE, "libcmpc.so.stamp")
+
+
+def source_hash():
+    """sha256 over the sources and the compile flags: what the stamp next to libcmpc.so records."""
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB):
+    """The library is current iff its stamp holds the hash of today's sources (file times are not trusted: a
+    prebuilt libcmpc.so travels with repository snapshots and may be newer than a fresh checkout's sources)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_timing():
@@ -54,6 +71,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libcmpc.so")
     with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:
         f.write(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

@@ -305,7 +305,7 @@ riccati2_lockstep_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, in
 // the work-list of the condensed kernel.  ctl: [0] work-list length, [1] cursor of the condensed kernel, [2] robot cursor.
 constexpr int kWrThreads = 128;
 __global__ void __launch_bounds__(kWrThreads, 2)
-wrench_pdas_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm, wr::D2* __restrict__ gains,
+wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __restrict__ gains,
                    int* __restrict__ worklist, int* __restrict__ ctl, size_t robot_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     wr::Tab* tb = reinterpret_cast<wr::Tab*>(smem);
@@ -315,15 +315,13 @@ wrench_pdas_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm
     const size_t tab_bytes = (sizeof(wr::Tab) + 15) & ~(size_t)15;
     wr::Sh* sh = reinterpret_cast<wr::Sh*>(smem + tab_bytes + (size_t)rslot * robot_bytes);
     unsigned char* codes = wr::codes_of(sh);
-    const int N = bi.N;
+    const int N = bt.N;
     wr::TS ts[1];
     wr::Env e;
-    e.p = &p; e.tb = tb;
+    e.p = &p; e.tb = tb; e.bt = &bt; e.b = 0;
     e.gains = gains + (size_t)blockIdx.x * N * wr::GAIN_D2 * blockDim.x + threadIdx.x;
     e.gstride = blockDim.x;
-    e.dt = bi.dt; e.h = bi.dt * bi.dt / 2.0;
-    e.in = qp_in(bi, 0);
-    e.o = qp_out(bo, 0, N);
+    e.dt = bt.dt; e.h = bt.dt * bt.dt / 2.0;
     const int max_it = p.pdas_max_iter;
     int b = -1, it = 0, nst = 0;
     bool exhausted = false;
@@ -334,7 +332,7 @@ wrench_pdas_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm
         nb = __shfl_sync(0xffffffffu, nb, lane & ~3);
         bool fresh = false;
         if (need) {
-            if (nb < B) { b = nb; it = 0; fresh = true; e.in = qp_in(bi, b); e.o = qp_out(bo, b, N); }
+            if (nb < B) { b = nb; it = 0; fresh = true; e.b = b; }
             else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, b >= 0)) break;
@@ -349,12 +347,37 @@ wrench_pdas_kernel(Params p, BatchIn bi, BatchOut bo, int B, int nfmax, int warm
         const int fl = wr::forward_sweep(qlane, valid, ts, sh, e, cur, prev, next);
         const bool conv = valid && (pmin > 0.0) && !(fl & 1);
         if (valid && !conv && (!(pmin > 0.0) || (fl & 2) || it + 1 >= max_it)) fail = true;
-        if (__any_sync(0xffffffffu, conv)) {
-            const int ok = wr::epilogue(qlane, conv, ts, sh, e, cur, nst, it + 1, warm);
-            if (conv && !ok) fail = true;
-        }
-        if (fail && qlane == 0) worklist[atomicAdd(ctl, 1)] = b;
+        wr::mark_pending(qlane, conv, ts, e, nst, it + 1);
+        if (fail && qlane == 0) { worklist[atomicAdd(ctl, 1)] = b; bt.status[b] = wr::ST_HANDED_ON; }
         if (conv || fail) b = -1; else if (valid) ++it;
+    }
+}
+
+// Certificates and remaining outputs of the robots the sweep kernel settled: one quad per robot, no state carried
+// over from the sweeps -- everything is recomputed from X, u, y.  Robots whose certificate does not hold join the
+// work-list of the condensed kernel.
+constexpr int kWfThreads = 256;
+__global__ void __launch_bounds__(kWfThreads)
+wrench_finish_kernel(Params p, wr::Bat bt, int B, int warm, int* __restrict__ worklist, int* __restrict__ ctl) {
+    __shared__ wr::Tab tb;
+    __shared__ wr::ShF sf_all[kWfThreads / 4];
+    if (threadIdx.x < 16) wr::fill_tab(tb, p, threadIdx.x);
+    __syncthreads();
+    const int qlane = threadIdx.x & 3;
+    wr::ShF* sf = sf_all + (threadIdx.x >> 2);
+    wr::TS ts[1];
+    wr::Env e;
+    e.p = &p; e.tb = &tb; e.bt = &bt;
+    e.gains = nullptr; e.gstride = 0;
+    e.dt = bt.dt; e.h = bt.dt * bt.dt / 2.0;
+    const int per = blockDim.x >> 2;
+    for (int base = blockIdx.x * per; base < B; base += gridDim.x * per) {       // warp-uniform trip count
+        const int b = base + (threadIdx.x >> 2);
+        const bool valid = b < B && bt.status[b < B ? b : 0] == wr::ST_PENDING;
+        e.b = b < B ? b : 0;
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        const int ok = wr::finish_robot(qlane, valid, ts, sf, e, warm);
+        if (valid && !ok && qlane == 0) { worklist[atomicAdd(ctl, 1)] = b; bt.status[b] = wr::ST_HANDED_ON; }
     }
 }
 
@@ -528,6 +551,7 @@ struct cmpc_handle {
         double* gains = nullptr; size_t gain_bytes = 0;       // Riccati gains (pre-pass 1-3) or wrench gains (pre-pass 4)
         double* yg = nullptr;                                 // rows of large working sets, per CTA of the condensed kernel
         double* hp = nullptr;                                 // block-packed factor when it does not fit shared memory
+        double* xs = nullptr;                                 // predicted states (B,12N) when the caller does not ask for them
     };
     Slot slot[4];
     std::atomic<unsigned> slot_next{0};
@@ -619,7 +643,7 @@ int wrench_grid(const cmpc_handle* h, int B) {
     return want < cap ? want : cap;
 }
 
-struct SlotSizes { size_t worklist, ctl, gains, yg, hp, total; };
+struct SlotSizes { size_t worklist, ctl, gains, yg, hp, xs, total; };
 SlotSizes slot_sizes(const cmpc_handle* h, int B) {
     SlotSizes z;
     const int ctas = h->sm_count * 2;
@@ -634,13 +658,14 @@ SlotSizes slot_sizes(const cmpc_handle* h, int B) {
     if (hg > hs) hs = hg;
     if (hb > hs) hs = hb;
     z.hp = hs * ctas * sizeof(double);
-    z.total = 4 * (z.worklist + z.ctl + z.gains + z.yg + z.hp);
+    z.xs = (size_t)B * 12 * h->N * sizeof(double);
+    z.total = 4 * (z.worklist + z.ctl + z.gains + z.yg + z.hp + z.xs);
     return z;
 }
 
 void free_slots(cmpc_handle* h) {
     for (auto& q : h->slot) {
-        void* ptrs[] = {q.worklist, q.ctl, q.gains, q.yg, q.hp};
+        void* ptrs[] = {q.worklist, q.ctl, q.gains, q.yg, q.hp, q.xs};
         for (void* p : ptrs) if (p) cudaFree(p);
         q = cmpc_handle::Slot();
     }
@@ -661,6 +686,7 @@ int reserve_slots(cmpc_handle* h, int B) {
         q.gain_bytes = z.gains;
         if (z.yg) CU_TRY(cudaMalloc(&q.yg, z.yg));
         if (z.hp) CU_TRY(cudaMalloc(&q.hp, z.hp));
+        CU_TRY(cudaMalloc(&q.xs, z.xs));
     }
     h->reserved_batch = B;
     h->reserved_nfmax = h->nfmax;
@@ -949,8 +975,13 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 const int grid_w = wrench_grid(h, B);
                 if (smem_w <= h->smem_optin && (size_t)grid_w * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2) <= sl.gain_bytes) {
                     if (set_smem((const void*)wrench_pdas_kernel, smem_w, &h->attr_wrench)) return -1;
-                    wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bi, bo, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
+                    wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W};
+                    wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bt, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
                                                                          sl.worklist, sl.ctl, wr::robot_bytes(h->N));
+                    ++g_launches;
+                    CU_TRY(cudaGetLastError());
+                    const int per = kWfThreads / 4, want_f = (B + per - 1) / per, cap_w = h->sm_count * 16;
+                    wrench_finish_kernel<<<want_f < cap_w ? want_f : cap_w, kWfThreads, 0, st>>>(h->p, bt, B, warm, sl.worklist, sl.ctl);
                     launched = true;
                 }
             }

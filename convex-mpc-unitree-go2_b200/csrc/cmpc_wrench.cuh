@@ -19,8 +19,10 @@
 //     loop ends when the set repeats.  A sweep costs the same whatever the size of the working set.
 //
 // Thread a of a quad owns the block row a in {p, rpy, v, omega} of P (3 x 12, registers) and, in its second role,
-// foot a.  Exchanges inside the quad go through ~1.6 KB of shared memory per robot and __syncwarp; the 6 x 6 work is
-// done redundantly by the four threads (no exchange, no idle lanes).  Gains go to an L2-resident scratch.
+// foot a (its contribution to Lam_k, its force, multipliers and next working-set code).  Exchanges inside the quad go
+// through ~2.9 KB of shared memory per robot and __syncwarp; the 6 x 6 factorizations are done redundantly by the four
+// threads (no exchange, no idle lanes).  Gains go to an L2-resident scratch.  The certificate / remaining outputs of a
+// robot whose working set has settled are written by a second, fully parallel kernel (finish_robot).
 // The same source compiles for the host (tests/_emul): there the four threads of a quad run one after the other
 // between the synchronisation points.
 #pragma once
@@ -30,24 +32,33 @@ namespace cmpc {
 namespace wr {
 
 enum { PATH_WRENCH = 5 };
+enum { ST_PENDING = 3, ST_HANDED_ON = -100 };    // internal markers between the sweep kernel and the finish kernel
 constexpr unsigned char SWING = 255;
-constexpr int GAIN_D2 = 12;      // double2 slots per thread and stage: Ktil rows (9), kbar part (1), state (2)
+constexpr int GAIN_D2 = 10;      // double2 slots per thread and stage: Ktil rows (9), kbar part (1)
 
 #if defined(__CUDA_ARCH__)
 #define WR_Q_BEGIN { const int q = qlane; TS& t = ts[0];
 #define WR_Q_END }
 #define WR_SYNC() __syncwarp()
-#define WR_NTS 1
 #define WR_GQ 0          // e.gains already points at this thread's slots
 #else
 #define WR_Q_BEGIN for (int q = 0; q < 4; ++q) { TS& t = ts[q];
 #define WR_Q_END }
 #define WR_SYNC() ((void)0)
-#define WR_NTS 4
 #define WR_GQ q
 #endif
 
 struct alignas(16) D2 { double x, y; };
+
+// batch arrays (device pointers), layouts of include/cmpc.h
+struct Bat {
+    const double *x0, *x_ref, *r_foot, *I_world, *mass;
+    const uint64_t* mask;
+    double *u, *y, *rho, *X, *nu, *stats;
+    int32_t *status, *iters;
+    double dt;
+    int N, W;
+};
 
 // CTA-wide tables (shared memory): indices depend on the thread, so they must not sit in the constant bank
 struct Tab {
@@ -55,14 +66,22 @@ struct Tab {
     double sig[16];          // [leg][2 (fx tied) + (fy tied)] = 1 / (Rz + [fx tied] mu^2 Rx + [fy tied] mu^2 Ry)
 };
 
-// shared memory of one robot
+// shared memory of one robot (sweep kernel)
 struct Sh {
     double E1[72];           // backward: (P Bbar) blocks [a][i][c]; forward: x (12) | mu partials (24) | wrench partials (24)
-    double E3[12];           // backward: q ; epilogue: co-state
-    double E4[78];           // backward: rows of (D A) and d of the threads p, rpy ; reductions
+    double E3[12];           // backward: p
+    double FL[4 * 28];       // backward: contribution of foot j to Lam_k (21) and what_k (6); then rows of (D A) and d of
+                             // the threads p, rpy (2 x 39, after a synchronisation)
+    double PK[4 * 36];       // backward: the block rows of P while the 6 x 6 work needs the registers
     double cst[12];          // cy, sy, 1/m, Iinv[9]
-    double ring[2][24];      // inputs of a stage, prefetched: lever arms (12) | reference column (12)
+    double ring[2][12];      // lever arms of a stage, prefetched
     int flag[8];
+};
+// shared memory of one robot (finish kernel)
+struct ShF {
+    double nus[12];
+    double red[16];
+    double cst[12];
 };
 
 CMPC_HD size_t robot_bytes(int N) { return (sizeof(Sh) + (size_t)3 * 4 * N + 15) & ~(size_t)15; }
@@ -70,13 +89,14 @@ CMPC_HD unsigned char* codes_of(Sh* sh) { return reinterpret_cast<unsigned char*
 
 // per-thread state that lives across synchronisation points
 struct TS {
-    double P[36];            // block row a of P, P[i*12 + c]
+    double P[36];            // block row a of P, P[i*12 + c] (registers between phase 3 and phase 1; parked in Sh::PK otherwise)
     double pv[3];            // block a of p ; forward: block a of x
-    double lam[21];          // Lam_k, lower triangle
-    double wh[6];            // what_k
-    double qa[3];            // q_a, then d_a
-    double ax[3];            // forward: block a of A x_k
-    double red[4];           // epilogue partial reductions
+    double qa[3];            // d_a
+    double xr[3];            // reference entries of the stage (own rows)
+    double ax[3];            // forward: block a of A x_k ; finish: co-state block
+    double red[4];           // finish: partial reductions
+    double L[21], di[6], Ln[21], dn[6], gh[12], phiq[6];      // backward phase 2: factors and vectors of the stage
+    D2 gk[GAIN_D2];          // forward: gains of the current stage (loaded one stage ahead)
     int chg, cyc;
 };
 
@@ -110,6 +130,8 @@ CMPC_HD void cp_commit_wait() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 #endif
 }
+// 16-byte shared-memory load of two adjacent doubles (the compiler cannot prove the alignment itself)
+CMPC_HD D2 ld2(const double* p) { return *reinterpret_cast<const D2*>(p); }
 
 // foot projection for a working-set code: bit 0 fz pinned at fz_min, bits 1-2 fx (0 free, 1 = +mu fz, 2 = -mu fz),
 // bits 3-4 fy likewise; SWING = not in stance
@@ -194,12 +216,21 @@ CMPC_HD void lmul6(const double* L, const double* w, double* out) {
 struct Env {                 // what one quad needs to know about its robot (uniform inside the quad)
     const Params* p;
     const Tab* tb;
-    QpIn in;
-    QpOut o;
+    const Bat* bt;
+    int b;                   // robot
     D2* gains;               // this thread's slots: gains[(k * GAIN_D2 + e) * gstride]
     size_t gstride;
     double dt, h;
 };
+CMPC_HD const double* in_xref(const Env& e) { return e.bt->x_ref + (size_t)e.b * 12 * e.bt->N; }
+CMPC_HD const double* in_rfoot(const Env& e) { return e.bt->r_foot + (size_t)e.b * 12 * e.bt->N; }
+CMPC_HD double* out_u(const Env& e) { return e.bt->u + (size_t)e.b * 12 * e.bt->N; }
+CMPC_HD double* out_y(const Env& e) { return e.bt->y + (size_t)e.b * 28 * e.bt->N; }
+CMPC_HD double* out_X(const Env& e) { return e.bt->X + (size_t)e.b * 12 * e.bt->N; }
+CMPC_HD double* out_stats(const Env& e) { return e.bt->stats + (size_t)e.b * NSTAT; }
+CMPC_HD int stance_at(const Env& e, int leg, int k) {
+    return mask_bit(e.bt->mask ? e.bt->mask + (size_t)e.b * e.bt->W : nullptr, e.bt->N, leg, k);
+}
 
 // block a of  Bbar w
 CMPC_HD void bbar_rows(int a, const double* cst, double dt, double h, const double* w, double* out) {
@@ -212,41 +243,51 @@ CMPC_HD void bbar_rows(int a, const double* cst, double dt, double h, const doub
     out[1] = cf * (-sn * s0 + c * s1);
     out[2] = cf * s2;
 }
-
-// prefetch the inputs of a stage: lever arms of step kr, reference column kx (clamped by the caller)
-CMPC_HD void ring_issue(int q, Sh* sh, int slot, const QpIn& in, int kr, int kx) {
-    const int N = in.N;
+// out (6) = Bbar' v  for a 12-vector v in shared memory
+CMPC_HD void bbar_t(const double* cst, double dt, double h, const double* v, double* out) {
+    const double cy = cst[0], sy = cst[1], minv = cst[2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        cp8(&sh->ring[slot][3 * q + c], in.r_foot + (size_t)(3 * q + c) * N + kr);
-        cp8(&sh->ring[slot][12 + 3 * q + c], in.x_ref + (size_t)(3 * q + c) * N + kx);
-    }
+    for (int c = 0; c < 3; ++c) out[c] = minv * (h * v[c] + dt * v[6 + c]);
+    out[3] = h * (cy * v[3] - sy * v[4]) + dt * v[9];
+    out[4] = h * (sy * v[3] + cy * v[4]) + dt * v[10];
+    out[5] = h * v[5] + dt * v[11];
+}
+
+// prefetch the lever arms of step kr
+CMPC_HD void ring_issue(int q, Sh* sh, int slot, const Env& e, int kr) {
+    const int N = e.bt->N;
+    const double* rf = in_rfoot(e);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cp8(&sh->ring[slot][3 * q + c], rf + (size_t)(3 * q + c) * N + kr);
+}
+
+CMPC_HD void robot_consts(const Env& e, double* cst) {
+    DynCommon dc;
+    dyn_common(dc, in_xref(e), e.bt->N, e.bt->I_world + (size_t)e.b * 9, e.bt->mass[e.b], e.bt->dt);
+    cst[0] = dc.cy; cst[1] = dc.sy; cst[2] = dc.minv;
+    for (int i = 0; i < 9; ++i) cst[3 + i] = dc.Iinv[i];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // robot set-up: constants, initial working set (from the contact table, or from the previous duals when warm)
 // ------------------------------------------------------------------------------------------------------------------
 CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int warm) {
-    const int N = e.in.N;
+    const int N = e.bt->N;
     unsigned char* codes = codes_of(sh);
     int nst = 0;
     WR_Q_BEGIN
     (void)t; (void)q;
     if (valid) {
-        if (q == 0) {
-            DynCommon dc;
-            dyn_common(dc, e.in.x_ref, N, e.in.I_world, e.in.mass, e.in.dt);
-            sh->cst[0] = dc.cy; sh->cst[1] = dc.sy; sh->cst[2] = dc.minv;
-            for (int i = 0; i < 9; ++i) sh->cst[3 + i] = dc.Iinv[i];
-        }
+        if (q == 0) robot_consts(e, sh->cst);
+        const double* yo = out_y(e);
         for (int k = 0; k < N; ++k) {
-            const int st = mask_bit(e.in.mask, N, q, k);
+            const int st = stance_at(e, q, k);
             unsigned char c = SWING;
             if (st) {
                 c = 0;
                 if (warm) {
-                    const double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
-                    const int az = e.o.y[12 * k + 3 * q + 2] < 0.0;
+                    const double* yf = yo + 12 * N + 16 * k + 4 * q;
+                    const int az = yo[12 * k + 3 * q + 2] < 0.0;
                     const int ax = yf[0] > 0.0 ? 1 : (yf[1] > 0.0 ? 2 : 0);
                     const int ay = yf[2] > 0.0 ? 1 : (yf[3] > 0.0 ? 2 : 0);
                     c = (unsigned char)(az | (ax << 1) | (ay << 3));
@@ -267,69 +308,65 @@ CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int 
 // backward sweep for the working set cur.  Returns the smallest pivot seen (<= 0: not positive definite).
 // ------------------------------------------------------------------------------------------------------------------
 CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const unsigned char* cur) {
-    const int N = e.in.N;
+    const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
     const double dt = e.dt, h = e.h;
     double pmin = 1e300;
     // terminal cost and the first prefetch
     WR_Q_BEGIN
+    const double* xr = in_xref(e);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) t.P[i * 12 + c] = (c == 3 * q + i) ? tb.Q[3 * q + i] : 0.0;
-        t.pv[i] = -tb.Q[3 * q + i] * e.in.x_ref[(size_t)(3 * q + i) * N + (N - 1)];
+        t.pv[i] = -tb.Q[3 * q + i] * xr[(size_t)(3 * q + i) * N + (N - 1)];
     }
-    ring_issue(q, sh, (N - 1) & 1, e.in, N - 1, N >= 2 ? N - 2 : 0);
+    ring_issue(q, sh, (N - 1) & 1, e, N - 1);
     WR_Q_END
     for (int k = N - 1; k >= 0; --k) {
         const double* ring = sh->ring[k & 1];
         WR_Q_BEGIN
-        (void)t;
+        (void)t; (void)q;
         cp_commit_wait();
         WR_Q_END
         WR_SYNC();
-        // ---- phase 1: Lam_k, what_k (every thread, all four feet), own rows of P Bbar, q_a
+        // ---- phase 1: foot q's contribution to Lam_k / what_k, own rows of P Bbar, p_a; P is parked
         WR_Q_BEGIN
-        if (k > 0) ring_issue(q, sh, (k - 1) & 1, e.in, k - 1, k >= 2 ? k - 2 : 0);
+        if (k > 0) {
+            ring_issue(q, sh, (k - 1) & 1, e, k - 1);
+            const double* xr = in_xref(e);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) t.xr[i] = xr[(size_t)(3 * q + i) * N + (k - 1)];
+        }
         const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
-#pragma unroll
-        for (int i = 0; i < 21; ++i) t.lam[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) t.wh[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const FootP f = foot_proj(cur[4 * k + j], j, tb, p.mu, p.fz_min);
+        {
+            const FootP f = foot_proj(cur[4 * k + q], q, tb, p.mu, p.fz_min);
             double W[9], Wz[3];
-            foot_W(sh->cst + 3, ring + 3 * j, W);
+            foot_W(sh->cst + 3, ring + 3 * q, W);
 #pragma unroll
             for (int m = 0; m < 3; ++m) Wz[m] = W[m * 3] * f.zx + W[m * 3 + 1] * f.zy + W[m * 3 + 2];
             const double sx = f.sg * f.zx, sy_ = f.sg * f.zy;
-            t.lam[lt(0, 0)] += f.dx + sx * f.zx;
-            t.lam[lt(1, 0)] += sx * f.zy;
-            t.lam[lt(1, 1)] += f.dy + sy_ * f.zy;
-            t.lam[lt(2, 0)] += sx;
-            t.lam[lt(2, 1)] += sy_;
-            t.lam[lt(2, 2)] += f.sg;
+            double* o = sh->FL + q * 28;
+            o[lt(0, 0)] = f.dx + sx * f.zx;
+            o[lt(1, 0)] = sx * f.zy;
+            o[lt(1, 1)] = f.dy + sy_ * f.zy;
+            o[lt(2, 0)] = sx;
+            o[lt(2, 1)] = sy_;
+            o[lt(2, 2)] = f.sg;
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
-                t.lam[lt(3 + m, 0)] += f.dx * W[m * 3] + sx * Wz[m];
-                t.lam[lt(3 + m, 1)] += f.dy * W[m * 3 + 1] + sy_ * Wz[m];
-                t.lam[lt(3 + m, 2)] += f.sg * Wz[m];
                 const double a0 = f.dx * W[m * 3], a1 = f.dy * W[m * 3 + 1], a2 = f.sg * Wz[m];
+                o[lt(3 + m, 0)] = a0 + sx * Wz[m];
+                o[lt(3 + m, 1)] = a1 + sy_ * Wz[m];
+                o[lt(3 + m, 2)] = a2;
 #pragma unroll
-                for (int n = 0; n <= m; ++n) t.lam[lt(3 + m, 3 + n)] += a0 * W[n * 3] + a1 * W[n * 3 + 1] + a2 * Wz[n];
+                for (int n = 0; n <= m; ++n) o[lt(3 + m, 3 + n)] = a0 * W[n * 3] + a1 * W[n * 3 + 1] + a2 * Wz[n];
             }
-            t.wh[0] += f.fh * f.zx; t.wh[1] += f.fh * f.zy; t.wh[2] += f.fh;
+            o[21] = f.fh * f.zx; o[22] = f.fh * f.zy; o[23] = f.fh;
 #pragma unroll
-            for (int m = 0; m < 3; ++m) t.wh[3 + m] += f.fh * Wz[m];
+            for (int m = 0; m < 3; ++m) o[24 + m] = f.fh * Wz[m];
         }
-        // ghat = g + Bbar what
-        double gh[12];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, t.wh, gh + 3 * a);
-        gh[2] += -9.81 * h;
-        gh[8] += -9.81 * dt;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double* Pi = t.P + i * 12;
@@ -339,38 +376,66 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
             o[3] = h * (Pi[3] * cy - Pi[4] * sy) + dt * Pi[9];
             o[4] = h * (Pi[3] * sy + Pi[4] * cy) + dt * Pi[10];
             o[5] = h * Pi[5] + dt * Pi[11];
-            double s = t.pv[i];
+            sh->E3[3 * q + i] = t.pv[i];
+            if (k > 0) {
+                double* pk = sh->PK + q * 36 + i * 12;
 #pragma unroll
-            for (int c = 0; c < 12; ++c) s += Pi[c] * gh[c];
-            t.qa[i] = s;
-            sh->E3[3 * q + i] = s;
+                for (int c = 0; c < 12; c += 2) { D2 v; v.x = Pi[c]; v.y = Pi[c + 1]; *reinterpret_cast<D2*>(pk + c) = v; }
+            }
         }
         WR_Q_END
         WR_SYNC();
-        // ---- phase 2: 6 x 6 factorizations (every thread), gains, own rows of D = P - (P Bbar) Phi (P Bbar)', D A
+        // ---- phase 2a: 6 x 6 factorizations (every thread), vector part
         WR_Q_BEGIN
         const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
         const double* E1 = sh->E1;
-        double L[21], di[6];
+        double* L = t.L;
         {   // Gbar = Bbar' (P Bbar), lower triangle
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int c = 0; c <= r; ++c) L[lt(r, c)] = minv * (h * E1[0 * 18 + r * 6 + c] + dt * E1[2 * 18 + r * 6 + c]);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const double x0 = E1[18 + c], x1 = E1[18 + 6 + c], x2 = E1[18 + 12 + c];
-                const double r0 = h * (cy * x0 - sy * x1) + dt * E1[54 + c];
-                const double r1 = h * (sy * x0 + cy * x1) + dt * E1[54 + 6 + c];
-                const double r2 = h * x2 + dt * E1[54 + 12 + c];
-                if (c <= 3) L[lt(3, c)] = r0;
-                if (c <= 4) L[lt(4, c)] = r1;
-                L[lt(5, c)] = r2;
+            for (int c = 0; c < 6; c += 2) {
+                const D2 x0 = ld2(E1 + 18 + c), x1 = ld2(E1 + 18 + 6 + c), x2 = ld2(E1 + 18 + 12 + c);
+                const D2 w0 = ld2(E1 + 54 + c), w1 = ld2(E1 + 54 + 6 + c), w2 = ld2(E1 + 54 + 12 + c);
+                const double r0a = h * (cy * x0.x - sy * x1.x) + dt * w0.x, r0b = h * (cy * x0.y - sy * x1.y) + dt * w0.y;
+                const double r1a = h * (sy * x0.x + cy * x1.x) + dt * w1.x, r1b = h * (sy * x0.y + cy * x1.y) + dt * w1.y;
+                const double r2a = h * x2.x + dt * w2.x, r2b = h * x2.y + dt * w2.y;
+                if (c <= 3) L[lt(3, c)] = r0a;
+                if (c + 1 <= 3) L[lt(3, c + 1 <= 3 ? c + 1 : 0)] = r0b;
+                if (c <= 4) L[lt(4, c)] = r1a;
+                if (c + 1 <= 4) L[lt(4, c + 1 <= 4 ? c + 1 : 0)] = r1b;
+                L[lt(5, c)] = r2a;
+                L[lt(5, c + 1)] = r2b;
             }
         }
-        pmin = fmin(pmin, chol6(L, di));
-        double Ln[21], dn[6];
-        {   // Nn = I + L' Lam L, column by column
+        pmin = fmin(pmin, chol6(L, t.di));
+        {   // Lam_k and what_k from the four feet; Nn = I + L' Lam L, column by column
+            double lam[21], wh[6];
+            const double* F = sh->FL;
+#pragma unroll
+            for (int i = 0; i < 20; i += 2) {
+                const D2 a = ld2(F + i), b = ld2(F + 28 + i), c = ld2(F + 56 + i), d = ld2(F + 84 + i);
+                lam[i] = (a.x + b.x) + (c.x + d.x);
+                lam[i + 1] = (a.y + b.y) + (c.y + d.y);
+            }
+            {
+                const D2 a = ld2(F + 20), b = ld2(F + 28 + 20), c = ld2(F + 56 + 20), d = ld2(F + 84 + 20);
+                lam[20] = (a.x + b.x) + (c.x + d.x);
+                wh[0] = (a.y + b.y) + (c.y + d.y);
+            }
+#pragma unroll
+            for (int i = 22; i < 26; i += 2) {
+                const D2 a = ld2(F + i), b = ld2(F + 28 + i), c = ld2(F + 56 + i), d = ld2(F + 84 + i);
+                wh[i - 21] = (a.x + b.x) + (c.x + d.x);
+                wh[i - 20] = (a.y + b.y) + (c.y + d.y);
+            }
+            wh[5] = (F[26] + F[28 + 26]) + (F[56 + 26] + F[84 + 26]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, wh, t.gh + 3 * a);
+            t.gh[2] += -9.81 * h;
+            t.gh[8] += -9.81 * dt;
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 double tj[6];
@@ -378,7 +443,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
                 for (int r = 0; r < 6; ++r) {
                     double s = 0.0;
 #pragma unroll
-                    for (int m = j; m < 6; ++m) s += t.lam[r >= m ? lt(r, m) : lt(m, r)] * L[lt(m, j)];
+                    for (int m = j; m < 6; ++m) s += lam[r >= m ? lt(r, m) : lt(m, r)] * L[lt(m, j)];
                     tj[r] = s;
                 }
 #pragma unroll
@@ -386,77 +451,90 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
                     double s = (i == j) ? 1.0 : 0.0;
 #pragma unroll
                     for (int m = i; m < 6; ++m) s += L[lt(m, i)] * tj[m];
-                    Ln[lt(i, j)] = s;
+                    t.Ln[lt(i, j)] = s;
                 }
             }
         }
-        chol6(Ln, dn);
-        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
-        // vector part: bq = Bbar' q, kbar = Gam bq, phiq = Phi bq
-        double phiq[6];
+        chol6(t.Ln, t.dn);
+        // vector part: bq = Bbar' q = (P Bbar)' ghat + Bbar' p,  kbar = Gam bq,  phiq = Phi bq
         {
-            const double* qv = sh->E3;
             double y[6], w[6], kb[6];
+            bbar_t(sh->cst, dt, h, sh->E3, y);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) y[c] = minv * (h * qv[c] + dt * qv[6 + c]);
-            y[3] = h * (cy * qv[3] - sy * qv[4]) + dt * qv[9];
-            y[4] = h * (sy * qv[3] + cy * qv[4]) + dt * qv[10];
-            y[5] = h * qv[5] + dt * qv[11];
-            fsub6(L, di, y);
+            for (int r = 0; r < 12; ++r) {
+                const D2 a = ld2(E1 + r * 6), b = ld2(E1 + r * 6 + 2), c = ld2(E1 + r * 6 + 4);
+                y[0] += a.x * t.gh[r]; y[1] += a.y * t.gh[r]; y[2] += b.x * t.gh[r];
+                y[3] += b.y * t.gh[r]; y[4] += c.x * t.gh[r]; y[5] += c.y * t.gh[r];
+            }
+            fsub6(L, t.di, y);
 #pragma unroll
             for (int c = 0; c < 6; ++c) w[c] = y[c];
-            fsub6(Ln, dn, w);
-            bsub6(Ln, dn, w);
+            fsub6(t.Ln, t.dn, w);
+            bsub6(t.Ln, t.dn, w);
             lmul6(L, w, kb);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) phiq[c] = y[c] - w[c];
-            bsub6(L, di, phiq);
+            for (int c = 0; c < 6; ++c) t.phiq[c] = y[c] - w[c];
+            bsub6(L, t.di, t.phiq);
             D2 kk;
             kk.x = q == 0 ? kb[0] : (q == 1 ? kb[2] : (q == 2 ? kb[4] : 0.0));
             kk.y = q == 0 ? kb[1] : (q == 1 ? kb[3] : (q == 2 ? kb[5] : 0.0));
+            D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
             g[9 * e.gstride] = kk;
         }
+        WR_Q_END
+        WR_SYNC();            // everybody has read FL: its storage now takes the rows the threads v, omega need
+        // ---- phase 2b: gains, own rows of D = P - (P Bbar) Phi (P Bbar)' and D A, one row at a time
+        WR_Q_BEGIN
+        const double cy = sh->cst[0], sy = sh->cst[1];
+        const double* E1 = sh->E1;
         const double* own = E1 + q * 18;
+        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             double y[6], w[6], kt[6];
+            {
+                const D2 a = ld2(own + i * 6), b = ld2(own + i * 6 + 2), c = ld2(own + i * 6 + 4);
+                y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y;
+            }
+            double Pi[12];
+            if (k > 0) {      // d_a = q_a - (P Bbar)_a Phi bq,  q_a = P_a ghat + p_a
+                const double* pk = sh->PK + q * 36 + i * 12;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) y[c] = own[i * 6 + c];
-            fsub6(L, di, y);
+                for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); Pi[c] = v.x; Pi[c + 1] = v.y; }
+                double d = t.pv[i];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) d += Pi[c] * t.gh[c];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d -= y[c] * t.phiq[c];
+                t.qa[i] = d;
+            }
+            fsub6(t.L, t.di, y);
 #pragma unroll
             for (int c = 0; c < 6; ++c) w[c] = y[c];
-            fsub6(Ln, dn, w);
-            bsub6(Ln, dn, w);
-            lmul6(L, w, kt);
+            fsub6(t.Ln, t.dn, w);
+            bsub6(t.Ln, t.dn, w);
+            lmul6(t.L, w, kt);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { D2 v; v.x = kt[2 * c]; v.y = kt[2 * c + 1]; g[(3 * i + c) * e.gstride] = v; }
             if (k > 0) {
                 double z[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) z[c] = y[c] - w[c];
-                bsub6(L, di, z);
-                double* Pi = t.P + i * 12;
+                bsub6(t.L, t.di, z);
 #pragma unroll
                 for (int b = 0; b < 12; ++b) {
-                    double s = Pi[b];
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) s -= z[c] * E1[b * 6 + c];
-                    Pi[b] = s;
+                    const D2 a = ld2(E1 + b * 6), bb = ld2(E1 + b * 6 + 2), c = ld2(E1 + b * 6 + 4);
+                    Pi[b] -= z[0] * a.x + z[1] * a.y + z[2] * bb.x + z[3] * bb.y + z[4] * c.x + z[5] * c.y;
                 }
-                double d = t.qa[i];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) d -= own[i * 6 + c] * phiq[c];
-                t.qa[i] = d;
                 // D A (own row)
                 Pi[6] += dt * Pi[0]; Pi[7] += dt * Pi[1]; Pi[8] += dt * Pi[2];
                 Pi[9] += dt * (cy * Pi[3] - sy * Pi[4]);
                 Pi[10] += dt * (sy * Pi[3] + cy * Pi[4]);
                 Pi[11] += dt * Pi[5];
-                if (q < 2) {
+                double* pk = sh->PK + q * 36 + i * 12;
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) sh->E4[q * 39 + i * 12 + c] = Pi[c];
-                    sh->E4[q * 39 + 36 + i] = d;
-                }
+                for (int c = 0; c < 12; c += 2) { D2 v; v.x = Pi[c]; v.y = Pi[c + 1]; *reinterpret_cast<D2*>(pk + c) = v; }
+                if (q < 2) sh->FL[q * 39 + 36 + i] = t.qa[i];
             }
         }
         WR_Q_END
@@ -466,26 +544,25 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         WR_Q_BEGIN
         const double dtc = q >= 2 ? dt : 0.0;
         const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
-        const double* X = sh->E4 + (q & 1) * 39;
-#pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            const double x0 = X[c], x1 = X[12 + c], x2 = X[24 + c];
-            t.P[c] += dtc * (rc * x0 - rs * x1);
-            t.P[12 + c] += dtc * (rs * x0 + rc * x1);
-            t.P[24 + c] += dtc * x2;
-        }
-        const double d0 = X[36], d1 = X[37], d2 = X[38];
-        const double a0 = t.qa[0] + dtc * (rc * d0 - rs * d1), a1 = t.qa[1] + dtc * (rs * d0 + rc * d1), a2 = t.qa[2] + dtc * d2;
+        const double* X = sh->PK + (q & 1) * 36;          // rows of the partner block (p for v, rpy for omega)
+        const double* O = sh->PK + q * 36;
         const double q0 = tb.Q[3 * q], q1 = tb.Q[3 * q + 1], q2 = tb.Q[3 * q + 2];
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {       // selects: P is a register array, its indices must be compile-time constants
-            t.P[c] += (c == 3 * q) ? q0 : 0.0;
-            t.P[12 + c] += (c == 3 * q + 1) ? q1 : 0.0;
-            t.P[24 + c] += (c == 3 * q + 2) ? q2 : 0.0;
+        for (int c = 0; c < 12; c += 2) {       // selects: P is a register array, its indices must be compile-time constants
+            const D2 x0 = ld2(X + c), x1 = ld2(X + 12 + c), x2 = ld2(X + 24 + c);
+            const D2 o0 = ld2(O + c), o1 = ld2(O + 12 + c), o2 = ld2(O + 24 + c);
+            t.P[c] = o0.x + dtc * (rc * x0.x - rs * x1.x) + ((c == 3 * q) ? q0 : 0.0);
+            t.P[c + 1] = o0.y + dtc * (rc * x0.y - rs * x1.y) + ((c + 1 == 3 * q) ? q0 : 0.0);
+            t.P[12 + c] = o1.x + dtc * (rs * x0.x + rc * x1.x) + ((c == 3 * q + 1) ? q1 : 0.0);
+            t.P[12 + c + 1] = o1.y + dtc * (rs * x0.y + rc * x1.y) + ((c + 1 == 3 * q + 1) ? q1 : 0.0);
+            t.P[24 + c] = o2.x + dtc * x2.x + ((c == 3 * q + 2) ? q2 : 0.0);
+            t.P[24 + c + 1] = o2.y + dtc * x2.y + ((c + 1 == 3 * q + 2) ? q2 : 0.0);
         }
-        t.pv[0] = a0 - q0 * ring[12 + 3 * q + 0];
-        t.pv[1] = a1 - q1 * ring[12 + 3 * q + 1];
-        t.pv[2] = a2 - q2 * ring[12 + 3 * q + 2];
+        const double* D = sh->FL + (q & 1) * 39 + 36;
+        const double d0 = D[0], d1 = D[1], d2 = D[2];
+        t.pv[0] = t.qa[0] + dtc * (rc * d0 - rs * d1) - q0 * t.xr[0];
+        t.pv[1] = t.qa[1] + dtc * (rs * d0 + rc * d1) - q1 * t.xr[1];
+        t.pv[2] = t.qa[2] + dtc * d2 - q2 * t.xr[2];
         WR_Q_END
     }
     WR_SYNC();
@@ -493,12 +570,12 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward sweep: states, forces, multipliers, next working set.  Writes forces / stance duals to o.u / o.y when
-// `valid`.  Returns bit 0: the working set changed, bit 1: the new set equals `prev` (a 2-cycle).
+// forward sweep: states, forces, multipliers, next working set.  Writes forces / stance duals / states to the output
+// arrays when `valid`.  Returns bit 0: the working set changed, bit 1: the new set equals `prev` (a 2-cycle).
 // ------------------------------------------------------------------------------------------------------------------
 CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur,
                           const unsigned char* prev, unsigned char* next) {
-    const int N = e.in.N;
+    const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
     const double dt = e.dt, h = e.h;
@@ -507,11 +584,16 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     double* mup = sh->E1 + 12;
     double* wp = sh->E1 + 36;
     WR_Q_BEGIN
+    const double* x0 = e.bt->x0 + (size_t)e.b * 12;
+    const double* rf = in_rfoot(e);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) t.pv[i] = e.in.x0[3 * q + i];
+    for (int i = 0; i < 3; ++i) t.pv[i] = x0[3 * q + i];
     t.chg = 0; t.cyc = 1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cp8(&sh->ring[0][3 * q + c], e.in.r_foot + (size_t)(3 * q + c) * N);
+    for (int c = 0; c < 3; ++c) cp8(&sh->ring[0][3 * q + c], rf + (size_t)(3 * q + c) * N);
+    const D2* g = e.gains + WR_GQ;
+#pragma unroll
+    for (int i = 0; i < GAIN_D2; ++i) t.gk[i] = g[i * e.gstride];
     WR_Q_END
     for (int k = 0; k < N; ++k) {
         double* ring = sh->ring[k & 1];
@@ -522,20 +604,20 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         for (int i = 0; i < 3; ++i) xs[3 * q + i] = t.pv[i];
         WR_Q_END
         WR_SYNC();
-        // ---- F2: A x (own block), partial wrench co-state
+        // ---- F2: A x (own block), partial wrench co-state; gains of the next stage
         WR_Q_BEGIN
         if (k + 1 < N) {
+            const double* rf = in_rfoot(e);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) cp8(&sh->ring[(k + 1) & 1][3 * q + c], e.in.r_foot + (size_t)(3 * q + c) * N + k + 1);
+            for (int c = 0; c < 3; ++c) cp8(&sh->ring[(k + 1) & 1][3 * q + c], rf + (size_t)(3 * q + c) * N + k + 1);
         }
-        const D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
         const double dtf = q < 2 ? dt : 0.0;
         const double rc = q == 1 ? sh->cst[0] : 1.0, rs = q == 1 ? sh->cst[1] : 0.0;
         const double* X = xs + 3 * (q | 2);
         t.ax[0] = t.pv[0] + dtf * (rc * X[0] + rs * X[1]);
         t.ax[1] = t.pv[1] + dtf * (-rs * X[0] + rc * X[1]);
         t.ax[2] = t.pv[2] + dtf * X[2];
-        const D2 kk = g[9 * e.gstride];
+        const D2 kk = t.gk[9];
         double mp[6];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { mp[2 * c] = (q == c) ? kk.x : 0.0; mp[2 * c + 1] = (q == c) ? kk.y : 0.0; }
@@ -543,12 +625,17 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const D2 v = g[(3 * i + c) * e.gstride];
+                const D2 v = t.gk[3 * i + c];
                 mp[2 * c] += v.x * t.ax[i];
                 mp[2 * c + 1] += v.y * t.ax[i];
             }
 #pragma unroll
         for (int c = 0; c < 6; ++c) mup[q * 6 + c] = mp[c];
+        if (k + 1 < N) {
+            const D2* g = e.gains + WR_GQ + (size_t)(k + 1) * GAIN_D2 * e.gstride;
+#pragma unroll
+            for (int i = 0; i < GAIN_D2; ++i) t.gk[i] = g[i * e.gstride];
+        }
         WR_Q_END
         WR_SYNC();
         // ---- F3: foot q -- force, multipliers, next code, wrench contribution
@@ -589,10 +676,11 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         t.chg |= (nc != code);
         t.cyc &= (nc == prev[4 * k + q]);
         if (valid) {
-            double* uo = e.o.u + 12 * k + 3 * q;
+            double* uo = out_u(e) + 12 * k + 3 * q;
+            double* yo = out_y(e);
             uo[0] = fo[0]; uo[1] = fo[1]; uo[2] = fo[2];
-            if (code != SWING) e.o.y[12 * k + 3 * q + 2] = -l5[0];
-            double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
+            if (code != SWING) yo[12 * k + 3 * q + 2] = -l5[0];
+            double* yf = yo + 12 * N + 16 * k + 4 * q;
             yf[0] = l5[1]; yf[1] = l5[2]; yf[2] = l5[3]; yf[3] = l5[4];
         }
 #pragma unroll
@@ -611,11 +699,10 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         t.pv[0] = t.ax[0] + bw[0];
         t.pv[1] = t.ax[1] + bw[1];
         t.pv[2] = t.ax[2] + bw[2] + (q == 0 ? -9.81 * h : (q == 2 ? -9.81 * dt : 0.0));
-        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
-        D2 a; a.x = t.pv[0]; a.y = t.pv[1];
-        D2 b; b.x = t.pv[2]; b.y = 0.0;
-        g[10 * e.gstride] = a;
-        g[11 * e.gstride] = b;
+        if (valid) {
+            double* Xo = out_X(e) + 12 * k + 3 * q;
+            Xo[0] = t.pv[0]; Xo[1] = t.pv[1]; Xo[2] = t.pv[2];
+        }
         WR_Q_END
     }
     WR_SYNC();
@@ -630,40 +717,56 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     return res;
 }
 
+// A robot whose working set has settled: mark it for the finish kernel.
+CMPC_HD void mark_pending(int qlane, bool conv, TS* ts, const Env& e, int nst, int sweeps) {
+    WR_Q_BEGIN
+    (void)t;
+    if (conv && q == 0) {
+        e.bt->status[e.b] = ST_PENDING;
+        double* st = out_stats(e);
+        st[3] = (double)(3 * nst);
+        st[6] = (double)(sweeps - 1);
+    }
+    WR_Q_END
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// epilogue of a robot whose working set has settled: co-states, stationarity and feasibility from first principles
-// (independent of the factorizations), the remaining outputs in the reference's layouts.  Returns 1 if accepted.
+// Finish (its own kernel, one quad per robot at full occupancy): co-states, stationarity and feasibility from first
+// principles -- X, u, y as written by the forward sweep, independent of the factorizations -- and the remaining outputs
+// in the reference's layouts.  Returns 1 if the certificate holds (status / statistics written), else 0.
 // ------------------------------------------------------------------------------------------------------------------
-CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur, int nst, int sweeps,
-                     int warm) {
-    const int N = e.in.N;
+CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, int warm) {
+    const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
     const double dt = e.dt, h = e.h;
-    double* nus = sh->E3;
+    double* nus = sf->nus;
     WR_Q_BEGIN
+    if (valid && q == 0) robot_consts(e, sf->cst);
     t.red[0] = 0.0; t.red[1] = 0.0; t.red[2] = 0.0; t.red[3] = 0.0;       // rd, rp, objective part, active rows
     t.ax[0] = 0.0; t.ax[1] = 0.0; t.ax[2] = 0.0;                          // co-state block
+    nus[3 * q] = 0.0; nus[3 * q + 1] = 0.0; nus[3 * q + 2] = 0.0;
     WR_Q_END
+    WR_SYNC();
     for (int k = N - 1; k >= 0; --k) {
         WR_Q_BEGIN
-        const D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
-        const D2 a = g[10 * e.gstride], b = g[11 * e.gstride];
-        const double xk[3] = {a.x, a.y, b.x};
         const double dtc = (q >= 2 && k < N - 1) ? dt : 0.0;
-        const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
+        const double rc = q == 3 ? sf->cst[0] : 1.0, rs = q == 3 ? sf->cst[1] : 0.0;
         const double* X = nus + 3 * (q & 1);
         double s[3];
         s[0] = dtc * (rc * X[0] - rs * X[1]);
         s[1] = dtc * (rs * X[0] + rc * X[1]);
         s[2] = dtc * X[2];
+        if (valid) {
+            const double* xk = out_X(e) + 12 * k + 3 * q;
+            const double* xrp = in_xref(e);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double xr = valid ? e.in.x_ref[(size_t)(3 * q + i) * N + k] : 0.0;
-            const double dd = xk[i] - xr;
-            s[i] += (k < N - 1 ? t.ax[i] : 0.0) - 2.0 * tb.Q[3 * q + i] * dd;
-            t.red[2] += tb.Q[3 * q + i] * (dd * dd - xr * xr);
-            if (valid && e.o.X) e.o.X[12 * k + 3 * q + i] = xk[i];
+            for (int i = 0; i < 3; ++i) {
+                const double xr = xrp[(size_t)(3 * q + i) * N + k];
+                const double dd = xk[i] - xr;
+                s[i] += (k < N - 1 ? t.ax[i] : 0.0) - 2.0 * tb.Q[3 * q + i] * dd;
+                t.red[2] += tb.Q[3 * q + i] * (dd * dd - xr * xr);
+            }
         }
         t.qa[0] = s[0]; t.qa[1] = s[1]; t.qa[2] = s[2];
         WR_Q_END
@@ -673,29 +776,26 @@ CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const 
         for (int i = 0; i < 3; ++i) {
             t.ax[i] = t.qa[i];
             nus[3 * q + i] = t.qa[i];
-            if (valid && e.o.nu) e.o.nu[12 * k + 3 * q + i] = t.qa[i];
+            if (valid && e.bt->nu) e.bt->nu[(size_t)e.b * 12 * N + 12 * k + 3 * q + i] = t.qa[i];
         }
         WR_Q_END
         WR_SYNC();
         WR_Q_BEGIN
-        const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
-        double bn[6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) bn[c] = minv * (h * nus[c] + dt * nus[6 + c]);
-        bn[3] = h * (cy * nus[3] - sy * nus[4]) + dt * nus[9];
-        bn[4] = h * (sy * nus[3] + cy * nus[4]) + dt * nus[10];
-        bn[5] = h * nus[5] + dt * nus[11];
         if (valid) {
+            double bn[6];
+            bbar_t(sf->cst, dt, h, nus, bn);
             double r[3], W[9], s3[3];
+            const double* rf = in_rfoot(e);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) r[c] = e.in.r_foot[(size_t)(3 * q + c) * N + k];
-            foot_W(sh->cst + 3, r, W);
+            for (int c = 0; c < 3; ++c) r[c] = rf[(size_t)(3 * q + c) * N + k];
+            foot_W(sf->cst + 3, r, W);
 #pragma unroll
             for (int c = 0; c < 3; ++c) s3[c] = bn[c] + W[c] * bn[3] + W[3 + c] * bn[4] + W[6 + c] * bn[5];
-            if (cur[4 * k + q] != SWING) {
-                const double* f = e.o.u + 12 * k + 3 * q;
-                const double* yf = e.o.y + 12 * N + 16 * k + 4 * q;
-                const double l0 = -e.o.y[12 * k + 3 * q + 2];
+            double* yo = out_y(e);
+            if (stance_at(e, q, k)) {
+                const double* f = out_u(e) + 12 * k + 3 * q;
+                const double* yf = yo + 12 * N + 16 * k + 4 * q;
+                const double l0 = -yo[12 * k + 3 * q + 2];
                 const double atl[3] = {yf[0] - yf[1], yf[2] - yf[3], -l0 - p.mu * (yf[0] + yf[1] + yf[2] + yf[3])};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -707,12 +807,12 @@ CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const 
                 t.red[3] += (l0 > 0.0) + (yf[0] > 0.0) + (yf[1] > 0.0) + (yf[2] > 0.0) + (yf[3] > 0.0);
                 // multipliers must not be negative (they are > 0 on the working set by construction)
                 t.red[0] = fmax(t.red[0], fmax(fmax(-l0, -yf[0]), fmax(fmax(-yf[1], -yf[2]), -yf[3])));
-                e.o.y[12 * k + 3 * q] = 0.0;
-                e.o.y[12 * k + 3 * q + 1] = 0.0;
+                yo[12 * k + 3 * q] = 0.0;
+                yo[12 * k + 3 * q + 1] = 0.0;
             } else {
-                e.o.y[12 * k + 3 * q] = s3[0];
-                e.o.y[12 * k + 3 * q + 1] = s3[1];
-                e.o.y[12 * k + 3 * q + 2] = s3[2];
+                yo[12 * k + 3 * q] = s3[0];
+                yo[12 * k + 3 * q + 1] = s3[1];
+                yo[12 * k + 3 * q + 2] = s3[2];
             }
         }
         WR_Q_END
@@ -720,10 +820,10 @@ CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const 
     }
     WR_Q_BEGIN
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sh->E4[4 * q + i] = t.red[i];
+    for (int i = 0; i < 4; ++i) sf->red[4 * q + i] = t.red[i];
     WR_Q_END
     WR_SYNC();
-    const double* R4 = sh->E4;
+    const double* R4 = sf->red;
     const double rd = fmax(fmax(R4[0], R4[4]), fmax(R4[8], R4[12]));
     const double rp = fmax(fmax(R4[1], R4[5]), fmax(R4[9], R4[13]));
     const double obj = R4[2] + R4[6] + R4[10] + R4[14];
@@ -732,28 +832,29 @@ CMPC_HD int epilogue(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const 
     WR_Q_BEGIN
     (void)t;
     if (valid && ok && q == 0) {
-        const double rho = (warm && e.o.rho && *e.o.rho > 0.0) ? *e.o.rho : p.rho0;
-        if (e.o.rho) *e.o.rho = rho;
-        *e.o.status = ST_SOLVED;
-        *e.o.iters = 0;
-        e.o.stats[0] = fmax(rp, 0.0);
-        e.o.stats[1] = rd;
-        e.o.stats[2] = obj;
-        e.o.stats[3] = (double)(3 * nst);
-        e.o.stats[4] = na;
-        e.o.stats[5] = rho;
-        e.o.stats[6] = (double)(sweeps - 1);
-        e.o.stats[7] = (double)(sweeps > 1 ? (int)PATH_WRENCH : (int)PATH_RICCATI);
+        double* rho_p = e.bt->rho ? e.bt->rho + e.b : nullptr;
+        const double rho = (warm && rho_p && *rho_p > 0.0) ? *rho_p : p.rho0;
+        if (rho_p) *rho_p = rho;
+        double* st = out_stats(e);
+        const int sweeps = (int)st[6] + 1;
+        e.bt->status[e.b] = ST_SOLVED;
+        e.bt->iters[e.b] = 0;
+        st[0] = fmax(rp, 0.0);
+        st[1] = rd;
+        st[2] = obj;
+        st[4] = na;
+        st[5] = rho;
+        st[7] = (double)(sweeps > 1 ? (int)PATH_WRENCH : (int)PATH_RICCATI);
     }
     WR_Q_END
     WR_SYNC();
     return ok;
 }
 
-// One robot from set-up to outputs (host emulation; the device kernel in cmpc.cu interleaves these steps over the
+// One robot from set-up to outputs (host emulation; the device kernels in cmpc.cu interleave these steps over the
 // eight robots of a warp).  Returns 1 if finished here, 0 if the robot goes on to the condensed kernel.
-CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int warm, int* sweeps_out) {
-    const int N = e.in.N;
+CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, ShF* sf, const Env& e, int nfmax, int warm, int* sweeps_out) {
+    const int N = e.bt->N;
     unsigned char* codes = codes_of(sh);
     const int nst = init_robot(qlane, true, ts, sh, e, warm);
     if (sweeps_out) *sweeps_out = 0;
@@ -767,7 +868,10 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
         if (!(pmin > 0.0)) return 0;
         const int fl = forward_sweep(qlane, true, ts, sh, e, cur, prev, next);
         if (sweeps_out) *sweeps_out = it + 1;
-        if (!(fl & 1)) return epilogue(qlane, true, ts, sh, e, cur, nst, it + 1, warm);
+        if (!(fl & 1)) {
+            mark_pending(qlane, true, ts, e, nst, it + 1);
+            return finish_robot(qlane, true, ts, sf, e, warm);
+        }
         if (fl & 2) return 0;           // the new set is the one before: a 2-cycle
     }
     return 0;

@@ -192,23 +192,17 @@ int emul_wrench(const Params* p, int B, int N, int nfmax, const double* x0, cons
     wr::Tab tb;
     for (int i = 0; i < 16; ++i) wr::fill_tab(tb, *p, i);
     wr::TS ts[4];
+    wr::ShF sf;
+    std::vector<double> xs((size_t)B * 12 * N);
+    wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : xs.data(), nu, stats, status, iters, dt, N, (4 * N + 63) / 64};
     for (int b = 0; b < B; ++b) {
         wr::Env e;
-        e.p = p; e.tb = &tb;
-        e.in = make_in(b, N, nullptr, nullptr, nullptr, x0, x_ref, r_foot, I_world, mass, dt, mask);
-        e.o.u = u + (size_t)b * 12 * N;
-        e.o.y = y + (size_t)b * 28 * N;
-        e.o.rho = rho ? rho + b : nullptr;
-        e.o.X = X ? X + (size_t)b * 12 * N : nullptr;
-        e.o.nu = nu ? nu + (size_t)b * 12 * N : nullptr;
-        e.o.status = status + b;
-        e.o.iters = iters + b;
-        e.o.stats = stats + (size_t)b * NSTAT;
-        e.gains = gains.data();      // thread q uses gains[... * 4 + q]: see the offset below
+        e.p = p; e.tb = &tb; e.bt = &bt; e.b = b;
+        e.gains = gains.data();      // thread q uses gains[... * 4 + q]
         e.gstride = 4;
         e.dt = dt; e.h = dt * dt / 2.0;
         int sw = 0;
-        done[b] = wr::solve_robot(0, ts, sh, e, nfmax, warm, &sw);
+        done[b] = wr::solve_robot(0, ts, sh, &sf, e, nfmax, warm, &sw);
         sweeps[b] = sw;
     }
     return 0;
