@@ -324,7 +324,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
     e.dt = bt.dt; e.h = bt.dt * bt.dt / 2.0;
     const int max_it = p.pdas_max_iter;
     int b = -1, it = 0, nst = 0;
-    bool exhausted = false;
+    bool exhausted = false, single = false;
     for (;;) {
         const bool need = (b < 0) && !exhausted;
         int nb = -1;
@@ -332,7 +332,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         nb = __shfl_sync(0xffffffffu, nb, lane & ~3);
         bool fresh = false;
         if (need) {
-            if (nb < B) { b = nb; it = 0; fresh = true; e.b = b; }
+            if (nb < B) { b = nb; it = 0; single = false; fresh = true; e.b = b; }
             else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, b >= 0)) break;
@@ -345,39 +345,17 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         const unsigned char* prev = codes + (size_t)((it + 2) % 3) * 4 * N;
         const double pmin = wr::backward_sweep(qlane, ts, sh, e, cur);
         const int fl = wr::forward_sweep(qlane, valid, ts, sh, e, cur, prev, next);
-        const bool conv = valid && (pmin > 0.0) && !(fl & 1);
-        if (valid && !conv && (!(pmin > 0.0) || (fl & 2) || it + 1 >= max_it)) fail = true;
-        wr::mark_pending(qlane, conv, ts, e, nst, it + 1);
-        if (fail && qlane == 0) { worklist[atomicAdd(ctl, 1)] = b; bt.status[b] = wr::ST_HANDED_ON; }
-        if (conv || fail) b = -1; else if (valid) ++it;
-    }
-}
-
-// Certificates and remaining outputs of the robots the sweep kernel settled: one quad per robot, no state carried
-// over from the sweeps -- everything is recomputed from X, u, y.  Robots whose certificate does not hold join the
-// work-list of the condensed kernel.
-constexpr int kWfThreads = 256;
-__global__ void __launch_bounds__(kWfThreads)
-wrench_finish_kernel(Params p, wr::Bat bt, int B, int warm, int* __restrict__ worklist, int* __restrict__ ctl) {
-    __shared__ wr::Tab tb;
-    __shared__ wr::ShF sf_all[kWfThreads / 4];
-    if (threadIdx.x < 16) wr::fill_tab(tb, p, threadIdx.x);
-    __syncthreads();
-    const int qlane = threadIdx.x & 3;
-    wr::ShF* sf = sf_all + (threadIdx.x >> 2);
-    wr::TS ts[1];
-    wr::Env e;
-    e.p = &p; e.tb = &tb; e.bt = &bt;
-    e.gains = nullptr; e.gstride = 0;
-    e.dt = bt.dt; e.h = bt.dt * bt.dt / 2.0;
-    const int per = blockDim.x >> 2;
-    for (int base = blockIdx.x * per; base < B; base += gridDim.x * per) {       // warp-uniform trip count
-        const int b = base + (threadIdx.x >> 2);
-        const bool valid = b < B && bt.status[b < B ? b : 0] == wr::ST_PENDING;
-        e.b = b < B ? b : 0;
-        if (!__any_sync(0xffffffffu, valid)) continue;
-        const int ok = wr::finish_robot(qlane, valid, ts, sf, e, warm);
-        if (valid && !ok && qlane == 0) { worklist[atomicAdd(ctl, 1)] = b; bt.status[b] = wr::ST_HANDED_ON; }
+        if (valid && !(pmin > 0.0)) fail = true;
+        if (!single && (fl & 1) && ((fl & 2) || it + 1 >= max_it)) single = true;       // a 2-cycle or the budget: one row at a time
+        const bool conv = valid && !fail && (single ? !(fl & 4) : !(fl & 1));
+        if (valid && !conv && it + 1 >= max_it + wr::kSingleMax) fail = true;
+        if (__any_sync(0xffffffffu, conv)) {
+            const int ok = wr::finish_robot(qlane, conv, ts, sh, e, warm, nst, it + 1);
+            if (conv && !ok) fail = true;
+        }
+        wr::single_step(qlane, single && valid && !conv && !fail, ts, sh, cur, next, N);
+        if (fail && qlane == 0) worklist[atomicAdd(ctl, 1)] = b;
+        if ((conv && !fail) || fail) b = -1; else if (valid) ++it;
     }
 }
 
@@ -978,10 +956,6 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                     wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W};
                     wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bt, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
                                                                          sl.worklist, sl.ctl, wr::robot_bytes(h->N));
-                    ++g_launches;
-                    CU_TRY(cudaGetLastError());
-                    const int per = kWfThreads / 4, want_f = (B + per - 1) / per, cap_w = h->sm_count * 16;
-                    wrench_finish_kernel<<<want_f < cap_w ? want_f : cap_w, kWfThreads, 0, st>>>(h->p, bt, B, warm, sl.worklist, sl.ctl);
                     launched = true;
                 }
             }

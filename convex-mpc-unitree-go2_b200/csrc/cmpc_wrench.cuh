@@ -22,7 +22,8 @@
 // foot a (its contribution to Lam_k, its force, multipliers and next working-set code).  Exchanges inside the quad go
 // through ~2.9 KB of shared memory per robot and __syncwarp; the 6 x 6 factorizations are done redundantly by the four
 // threads (no exchange, no idle lanes).  Gains go to an L2-resident scratch.  The certificate / remaining outputs of a
-// robot whose working set has settled are written by a second, fully parallel kernel (finish_robot).
+// robot whose working set has settled are written by finish_robot (inputs prefetched with cp.async).  Working sets
+// that cycle under the primal-dual rule continue with single exchanges (one row dropped or added per sweep).
 // The same source compiles for the host (tests/_emul): there the four threads of a quad run one after the other
 // between the synchronisation points.
 #pragma once
@@ -32,7 +33,6 @@ namespace cmpc {
 namespace wr {
 
 enum { PATH_WRENCH = 5 };
-enum { ST_PENDING = 3, ST_HANDED_ON = -100 };    // internal markers between the sweep kernel and the finish kernel
 constexpr unsigned char SWING = 255;
 constexpr int GAIN_D2 = 10;      // double2 slots per thread and stage: Ktil rows (9), kbar part (1)
 
@@ -41,11 +41,13 @@ constexpr int GAIN_D2 = 10;      // double2 slots per thread and stage: Ktil row
 #define WR_Q_END }
 #define WR_SYNC() __syncwarp()
 #define WR_GQ 0          // e.gains already points at this thread's slots
+
 #else
 #define WR_Q_BEGIN for (int q = 0; q < 4; ++q) { TS& t = ts[q];
 #define WR_Q_END }
 #define WR_SYNC() ((void)0)
 #define WR_GQ q
+
 #endif
 
 struct alignas(16) D2 { double x, y; };
@@ -70,20 +72,14 @@ struct Tab {
 struct Sh {
     double E1[72];           // backward: (P Bbar) blocks [a][i][c]; forward: x (12) | mu partials (24) | wrench partials (24)
     double E3[12];           // backward: p
-    double FL[4 * 28];       // backward: contribution of foot j to Lam_k (21) and what_k (6); then rows of (D A) and d of
-                             // the threads p, rpy (2 x 39, after a synchronisation)
-    double PK[4 * 36];       // backward: the block rows of P while the 6 x 6 work needs the registers
+    double FL[4 * 28];       // backward: contribution of foot j to Lam_k (21) and what_k (6)
+    double D4[8];            // backward: d of the threads p, rpy
+    double PK[4 * 36];       // backward: the block rows of P while the 6 x 6 work needs the registers; finish: prefetched
+                             // inputs of a stage, 2 slots x 4 threads x 18 (x 3, xref 3, lever arm 3, force 3, duals 5)
     double cst[12];          // cy, sy, 1/m, Iinv[9]
     double ring[2][12];      // lever arms of a stage, prefetched
-    int flag[8];
+    int flag[8];             // [0..3] per-thread PDAS flags; [4] row to drop, [5] row to add (single exchange), -1 = none
 };
-// shared memory of one robot (finish kernel)
-struct ShF {
-    double nus[12];
-    double red[16];
-    double cst[12];
-};
-
 CMPC_HD size_t robot_bytes(int N) { return (sizeof(Sh) + (size_t)3 * 4 * N + 15) & ~(size_t)15; }
 CMPC_HD unsigned char* codes_of(Sh* sh) { return reinterpret_cast<unsigned char*>(sh) + sizeof(Sh); }
 
@@ -95,11 +91,11 @@ struct TS {
     double xr[3];            // reference entries of the stage (own rows)
     double ax[3];            // forward: block a of A x_k ; finish: co-state block
     double red[4];           // finish: partial reductions
-    double L[21], di[6], Ln[21], dn[6], gh[12], phiq[6];      // backward phase 2: factors and vectors of the stage
     D2 gk[GAIN_D2];          // forward: gains of the current stage (loaded one stage ahead)
     int chg, cyc;
+    double dworst, amost;    // forward: single-exchange candidates of this thread's foot (most negative multiplier, largest violation)
+    int didx, aidx;
 };
-
 CMPC_HD int lt(int i, int j) { return ((i * (i + 1)) >> 1) + j; }      // lower-triangle index, i >= j
 
 CMPC_HD double wr_rsqrt(double v) {
@@ -160,56 +156,85 @@ CMPC_HD void foot_W(const double* Ii, const double* r, double* W) {
     }
 }
 
+// The 6 x 6 kernels below work on register arrays: every index has to be a compile-time constant, so the triangular
+// loops are written column by column with the column as a template parameter (constant trip counts for the unroller).
+template <int J>
+CMPC_HD void chol6_col(double* G, double* di, double& pmin) {
+    double s = G[lt(J, J)];
+#pragma unroll
+    for (int m = 0; m < J; ++m) s -= G[lt(J, m)] * G[lt(J, m)];
+    pmin = fmin(pmin, s);
+    const double r = wr_rsqrt(s);
+    di[J] = r;
+    G[lt(J, J)] = s * r;
+#pragma unroll
+    for (int i = J + 1; i < 6; ++i) {
+        double v = G[lt(i, J)];
+#pragma unroll
+        for (int m = 0; m < J; ++m) v -= G[lt(i, m)] * G[lt(J, m)];
+        G[lt(i, J)] = v * r;
+    }
+}
 // in-place Cholesky of a 6 x 6 lower triangle; di = reciprocal diagonal.  Returns the smallest pivot.
 CMPC_HD double chol6(double* G, double* di) {
     double pmin = 1e300;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double s = G[lt(j, j)];
-#pragma unroll
-        for (int m = 0; m < j; ++m) s -= G[lt(j, m)] * G[lt(j, m)];
-        pmin = fmin(pmin, s);
-        const double r = wr_rsqrt(s);
-        di[j] = r;
-        G[lt(j, j)] = s * r;
-#pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            double v = G[lt(i, j)];
-#pragma unroll
-            for (int m = 0; m < j; ++m) v -= G[lt(i, m)] * G[lt(j, m)];
-            G[lt(i, j)] = v * r;
-        }
-    }
+    chol6_col<0>(G, di, pmin); chol6_col<1>(G, di, pmin); chol6_col<2>(G, di, pmin);
+    chol6_col<3>(G, di, pmin); chol6_col<4>(G, di, pmin); chol6_col<5>(G, di, pmin);
     return pmin;
+}
+template <int J>
+CMPC_HD void fsub6_row(const double* L, const double* di, double* y) {
+    double s = y[J];
+#pragma unroll
+    for (int m = 0; m < J; ++m) s -= L[lt(J, m)] * y[m];
+    y[J] = s * di[J];
 }
 // y <- L^-1 y
 CMPC_HD void fsub6(const double* L, const double* di, double* y) {
+    fsub6_row<0>(L, di, y); fsub6_row<1>(L, di, y); fsub6_row<2>(L, di, y);
+    fsub6_row<3>(L, di, y); fsub6_row<4>(L, di, y); fsub6_row<5>(L, di, y);
+}
+template <int J>
+CMPC_HD void bsub6_row(const double* L, const double* di, double* y) {
+    double s = y[J];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double s = y[j];
-#pragma unroll
-        for (int m = 0; m < j; ++m) s -= L[lt(j, m)] * y[m];
-        y[j] = s * di[j];
-    }
+    for (int m = J + 1; m < 6; ++m) s -= L[lt(m, J)] * y[m];
+    y[J] = s * di[J];
 }
 // y <- L^-T y
 CMPC_HD void bsub6(const double* L, const double* di, double* y) {
+    bsub6_row<5>(L, di, y); bsub6_row<4>(L, di, y); bsub6_row<3>(L, di, y);
+    bsub6_row<2>(L, di, y); bsub6_row<1>(L, di, y); bsub6_row<0>(L, di, y);
+}
+template <int J>
+CMPC_HD void lmul6_row(const double* L, const double* w, double* out) {
+    double s = 0.0;
 #pragma unroll
-    for (int j = 5; j >= 0; --j) {
-        double s = y[j];
-#pragma unroll
-        for (int m = j + 1; m < 6; ++m) s -= L[lt(m, j)] * y[m];
-        y[j] = s * di[j];
-    }
+    for (int m = 0; m <= J; ++m) s += L[lt(J, m)] * w[m];
+    out[J] = s;
 }
 // out = L w
 CMPC_HD void lmul6(const double* L, const double* w, double* out) {
+    lmul6_row<0>(L, w, out); lmul6_row<1>(L, w, out); lmul6_row<2>(L, w, out);
+    lmul6_row<3>(L, w, out); lmul6_row<4>(L, w, out); lmul6_row<5>(L, w, out);
+}
+// column J of Nn = I + L' Lam L  (lower triangle)
+template <int J>
+CMPC_HD void nn_col(const double* lam, const double* L, double* Ln) {
+    double tj[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    for (int r = 0; r < 6; ++r) {
         double s = 0.0;
 #pragma unroll
-        for (int m = 0; m <= j; ++m) s += L[lt(j, m)] * w[m];
-        out[j] = s;
+        for (int m = J; m < 6; ++m) s += lam[r >= m ? lt(r, m) : lt(m, r)] * L[lt(m, J)];
+        tj[r] = s;
+    }
+#pragma unroll
+    for (int i = J; i < 6; ++i) {
+        double s = (i == J) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 5; m >= 0; --m) if (m >= i) s += L[lt(m >= i ? m : i, i)] * tj[m];
+        Ln[lt(i, J)] = s;
     }
 }
 
@@ -385,34 +410,14 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         }
         WR_Q_END
         WR_SYNC();
-        // ---- phase 2a: 6 x 6 factorizations (every thread), vector part
+        // ---- phase 2: 6 x 6 factorizations (every thread), vector part, gains, own rows of D = P - (P Bbar) Phi (P Bbar)' and D A
         WR_Q_BEGIN
         const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
         const double* E1 = sh->E1;
-        double* L = t.L;
-        {   // Gbar = Bbar' (P Bbar), lower triangle
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) L[lt(r, c)] = minv * (h * E1[0 * 18 + r * 6 + c] + dt * E1[2 * 18 + r * 6 + c]);
-#pragma unroll
-            for (int c = 0; c < 6; c += 2) {
-                const D2 x0 = ld2(E1 + 18 + c), x1 = ld2(E1 + 18 + 6 + c), x2 = ld2(E1 + 18 + 12 + c);
-                const D2 w0 = ld2(E1 + 54 + c), w1 = ld2(E1 + 54 + 6 + c), w2 = ld2(E1 + 54 + 12 + c);
-                const double r0a = h * (cy * x0.x - sy * x1.x) + dt * w0.x, r0b = h * (cy * x0.y - sy * x1.y) + dt * w0.y;
-                const double r1a = h * (sy * x0.x + cy * x1.x) + dt * w1.x, r1b = h * (sy * x0.y + cy * x1.y) + dt * w1.y;
-                const double r2a = h * x2.x + dt * w2.x, r2b = h * x2.y + dt * w2.y;
-                if (c <= 3) L[lt(3, c)] = r0a;
-                if (c + 1 <= 3) L[lt(3, c + 1 <= 3 ? c + 1 : 0)] = r0b;
-                if (c <= 4) L[lt(4, c)] = r1a;
-                if (c + 1 <= 4) L[lt(4, c + 1 <= 4 ? c + 1 : 0)] = r1b;
-                L[lt(5, c)] = r2a;
-                L[lt(5, c + 1)] = r2b;
-            }
-        }
-        pmin = fmin(pmin, chol6(L, t.di));
-        {   // Lam_k and what_k from the four feet; Nn = I + L' Lam L, column by column
-            double lam[21], wh[6];
+        const double* own = E1 + q * 18;
+        double lam[21], bq[6];
+        {   // Lam_k and what_k from the four feet; ghat; q_a = P_a ghat + p_a; bq = Bbar'q = (P Bbar)' ghat + Bbar' p
+            double wh[6], gh[12];
             const double* F = sh->FL;
 #pragma unroll
             for (int i = 0; i < 20; i += 2) {
@@ -433,62 +438,73 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
             }
             wh[5] = (F[26] + F[28 + 26]) + (F[56 + 26] + F[84 + 26]);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, wh, t.gh + 3 * a);
-            t.gh[2] += -9.81 * h;
-            t.gh[8] += -9.81 * dt;
+            for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, wh, gh + 3 * a);
+            gh[2] += -9.81 * h;
+            gh[8] += -9.81 * dt;
+            if (k > 0) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                double tj[6];
+                for (int i = 0; i < 3; ++i) {
+                    const double* pk = sh->PK + q * 36 + i * 12;
+                    double d = t.pv[i];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int m = j; m < 6; ++m) s += lam[r >= m ? lt(r, m) : lt(m, r)] * L[lt(m, j)];
-                    tj[r] = s;
-                }
-#pragma unroll
-                for (int i = j; i < 6; ++i) {
-                    double s = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int m = i; m < 6; ++m) s += L[lt(m, i)] * tj[m];
-                    t.Ln[lt(i, j)] = s;
+                    for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); d += v.x * gh[c] + v.y * gh[c + 1]; }
+                    t.qa[i] = d;
                 }
             }
-        }
-        chol6(t.Ln, t.dn);
-        // vector part: bq = Bbar' q = (P Bbar)' ghat + Bbar' p,  kbar = Gam bq,  phiq = Phi bq
-        {
-            double y[6], w[6], kb[6];
-            bbar_t(sh->cst, dt, h, sh->E3, y);
+            bbar_t(sh->cst, dt, h, sh->E3, bq);
 #pragma unroll
             for (int r = 0; r < 12; ++r) {
                 const D2 a = ld2(E1 + r * 6), b = ld2(E1 + r * 6 + 2), c = ld2(E1 + r * 6 + 4);
-                y[0] += a.x * t.gh[r]; y[1] += a.y * t.gh[r]; y[2] += b.x * t.gh[r];
-                y[3] += b.y * t.gh[r]; y[4] += c.x * t.gh[r]; y[5] += c.y * t.gh[r];
+                bq[0] += a.x * gh[r]; bq[1] += a.y * gh[r]; bq[2] += b.x * gh[r];
+                bq[3] += b.y * gh[r]; bq[4] += c.x * gh[r]; bq[5] += c.y * gh[r];
             }
-            fsub6(L, t.di, y);
+        }
+        double L[21], di[6];
+        {   // Gbar = Bbar' (P Bbar), lower triangle
 #pragma unroll
-            for (int c = 0; c < 6; ++c) w[c] = y[c];
-            fsub6(t.Ln, t.dn, w);
-            bsub6(t.Ln, t.dn, w);
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) L[lt(r, c)] = minv * (h * E1[0 * 18 + r * 6 + c] + dt * E1[2 * 18 + r * 6 + c]);
+#pragma unroll
+            for (int c = 0; c < 6; c += 2) {
+                const D2 x0 = ld2(E1 + 18 + c), x1 = ld2(E1 + 18 + 6 + c), x2 = ld2(E1 + 18 + 12 + c);
+                const D2 w0 = ld2(E1 + 54 + c), w1 = ld2(E1 + 54 + 6 + c), w2 = ld2(E1 + 54 + 12 + c);
+                const double r0a = h * (cy * x0.x - sy * x1.x) + dt * w0.x, r0b = h * (cy * x0.y - sy * x1.y) + dt * w0.y;
+                const double r1a = h * (sy * x0.x + cy * x1.x) + dt * w1.x, r1b = h * (sy * x0.y + cy * x1.y) + dt * w1.y;
+                const double r2a = h * x2.x + dt * w2.x, r2b = h * x2.y + dt * w2.y;
+                if (c <= 3) L[lt(3, c)] = r0a;
+                if (c + 1 <= 3) L[lt(3, c + 1 <= 3 ? c + 1 : 0)] = r0b;
+                if (c <= 4) L[lt(4, c)] = r1a;
+                if (c + 1 <= 4) L[lt(4, c + 1 <= 4 ? c + 1 : 0)] = r1b;
+                L[lt(5, c)] = r2a;
+                L[lt(5, c + 1)] = r2b;
+            }
+        }
+        pmin = fmin(pmin, chol6(L, di));
+        double Ln[21], dn[6];
+        nn_col<0>(lam, L, Ln); nn_col<1>(lam, L, Ln); nn_col<2>(lam, L, Ln);        // Nn = I + L' Lam L
+        nn_col<3>(lam, L, Ln); nn_col<4>(lam, L, Ln); nn_col<5>(lam, L, Ln);
+        chol6(Ln, dn);
+        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        // vector part: kbar = Gam bq,  phiq = Phi bq
+        double phiq[6];
+        {
+            double w[6], kb[6];
+            fsub6(L, di, bq);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) w[c] = bq[c];
+            fsub6(Ln, dn, w);
+            bsub6(Ln, dn, w);
             lmul6(L, w, kb);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) t.phiq[c] = y[c] - w[c];
-            bsub6(L, t.di, t.phiq);
+            for (int c = 0; c < 6; ++c) phiq[c] = bq[c] - w[c];
+            bsub6(L, di, phiq);
             D2 kk;
             kk.x = q == 0 ? kb[0] : (q == 1 ? kb[2] : (q == 2 ? kb[4] : 0.0));
             kk.y = q == 0 ? kb[1] : (q == 1 ? kb[3] : (q == 2 ? kb[5] : 0.0));
-            D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
             g[9 * e.gstride] = kk;
         }
-        WR_Q_END
-        WR_SYNC();            // everybody has read FL: its storage now takes the rows the threads v, omega need
-        // ---- phase 2b: gains, own rows of D = P - (P Bbar) Phi (P Bbar)' and D A, one row at a time
-        WR_Q_BEGIN
-        const double cy = sh->cst[0], sy = sh->cst[1];
-        const double* E1 = sh->E1;
-        const double* own = E1 + q * 18;
-        D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
+        // gains and the rows of D, one row at a time
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             double y[6], w[6], kt[6];
@@ -496,31 +512,30 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
                 const D2 a = ld2(own + i * 6), b = ld2(own + i * 6 + 2), c = ld2(own + i * 6 + 4);
                 y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y;
             }
-            double Pi[12];
-            if (k > 0) {      // d_a = q_a - (P Bbar)_a Phi bq,  q_a = P_a ghat + p_a
-                const double* pk = sh->PK + q * 36 + i * 12;
+            if (k > 0) {      // d_a = q_a - (P Bbar)_a Phi bq
+                double d = t.qa[i];
 #pragma unroll
-                for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); Pi[c] = v.x; Pi[c + 1] = v.y; }
-                double d = t.pv[i];
-#pragma unroll
-                for (int c = 0; c < 12; ++c) d += Pi[c] * t.gh[c];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) d -= y[c] * t.phiq[c];
+                for (int c = 0; c < 6; ++c) d -= y[c] * phiq[c];
                 t.qa[i] = d;
+                if (q < 2) sh->D4[q * 4 + i] = d;
             }
-            fsub6(t.L, t.di, y);
+            fsub6(L, di, y);
 #pragma unroll
             for (int c = 0; c < 6; ++c) w[c] = y[c];
-            fsub6(t.Ln, t.dn, w);
-            bsub6(t.Ln, t.dn, w);
-            lmul6(t.L, w, kt);
+            fsub6(Ln, dn, w);
+            bsub6(Ln, dn, w);
+            lmul6(L, w, kt);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { D2 v; v.x = kt[2 * c]; v.y = kt[2 * c + 1]; g[(3 * i + c) * e.gstride] = v; }
             if (k > 0) {
                 double z[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) z[c] = y[c] - w[c];
-                bsub6(t.L, t.di, z);
+                bsub6(L, di, z);
+                double* pk = sh->PK + q * 36 + i * 12;
+                double Pi[12];
+#pragma unroll
+                for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); Pi[c] = v.x; Pi[c + 1] = v.y; }
 #pragma unroll
                 for (int b = 0; b < 12; ++b) {
                     const D2 a = ld2(E1 + b * 6), bb = ld2(E1 + b * 6 + 2), c = ld2(E1 + b * 6 + 4);
@@ -531,10 +546,8 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
                 Pi[9] += dt * (cy * Pi[3] - sy * Pi[4]);
                 Pi[10] += dt * (sy * Pi[3] + cy * Pi[4]);
                 Pi[11] += dt * Pi[5];
-                double* pk = sh->PK + q * 36 + i * 12;
 #pragma unroll
                 for (int c = 0; c < 12; c += 2) { D2 v; v.x = Pi[c]; v.y = Pi[c + 1]; *reinterpret_cast<D2*>(pk + c) = v; }
-                if (q < 2) sh->FL[q * 39 + 36 + i] = t.qa[i];
             }
         }
         WR_Q_END
@@ -558,7 +571,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
             t.P[24 + c] = o2.x + dtc * x2.x + ((c == 3 * q + 2) ? q2 : 0.0);
             t.P[24 + c + 1] = o2.y + dtc * x2.y + ((c + 1 == 3 * q + 2) ? q2 : 0.0);
         }
-        const double* D = sh->FL + (q & 1) * 39 + 36;
+        const double* D = sh->D4 + (q & 1) * 4;
         const double d0 = D[0], d1 = D[1], d2 = D[2];
         t.pv[0] = t.qa[0] + dtc * (rc * d0 - rs * d1) - q0 * t.xr[0];
         t.pv[1] = t.qa[1] + dtc * (rs * d0 + rc * d1) - q1 * t.xr[1];
@@ -589,6 +602,7 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
 #pragma unroll
     for (int i = 0; i < 3; ++i) t.pv[i] = x0[3 * q + i];
     t.chg = 0; t.cyc = 1;
+    t.dworst = -tol; t.amost = 1e-9; t.didx = -1; t.aidx = -1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) cp8(&sh->ring[0][3 * q + c], rf + (size_t)(3 * q + c) * N);
     const D2* g = e.gains + WR_GQ;
@@ -671,6 +685,17 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
             const int nx = (s1 > tol && s1 >= s2) ? 1 : ((s2 > tol && s2 > s1) ? 2 : 0);
             const int ny = (s3 > tol && s3 >= s4) ? 1 : ((s4 > tol && s4 > s3) ? 2 : 0);
             nc = (unsigned char)(nz | (nx << 1) | (ny << 3));
+            // single-exchange candidates (solve_active_set_fast, second phase): the most negative multiplier of the
+            // working set, the most violated row outside it (not the face opposite to an active one)
+            const double vv[5] = {p.fz_min - fo[2], fo[0] - p.mu * fo[2], -fo[0] - p.mu * fo[2], fo[1] - p.mu * fo[2], -fo[1] - p.mu * fo[2]};
+            const bool on[5] = {az != 0, ax == 1, ax == 2, ay == 1, ay == 2};
+            const bool free5[5] = {true, ax == 0, ax == 0, ay == 0, ay == 0};
+            const int base = 5 * (4 * k + q);
+#pragma unroll
+            for (int r5 = 0; r5 < 5; ++r5) {
+                if (on[r5]) { if (l5[r5] < t.dworst) { t.dworst = l5[r5]; t.didx = base + r5; } }
+                else if (free5[r5] && vv[r5] > t.amost) { t.amost = vv[r5]; t.aidx = base + r5; }
+            }
         }
         next[4 * k + q] = nc;
         t.chg |= (nc != code);
@@ -707,66 +732,121 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     }
     WR_SYNC();
     int res = 0;
+    double* cand = sh->E1 + 60;           // 4 x (value of the drop candidate, value of the add candidate)
+    int* candi = reinterpret_cast<int*>(sh->E1 + 68);
     WR_Q_BEGIN
     sh->flag[q] = t.chg | (t.cyc << 1);
+    cand[2 * q] = t.dworst; cand[2 * q + 1] = t.amost;
+    candi[2 * q] = t.didx; candi[2 * q + 1] = t.aidx;
     WR_Q_END
     WR_SYNC();
     res = (sh->flag[0] | sh->flag[1] | sh->flag[2] | sh->flag[3]) & 1;
     res |= (sh->flag[0] & sh->flag[1] & sh->flag[2] & sh->flag[3]) & 2;
+    {   // the same reduction in every thread: worst drop candidate, else best add candidate
+        double dw = 0.0, am = 0.0;
+        int di_ = -1, ai_ = -1;
+        for (int j = 0; j < 4; ++j) {
+            if (candi[2 * j] >= 0 && (di_ < 0 || cand[2 * j] < dw)) { dw = cand[2 * j]; di_ = candi[2 * j]; }
+            if (candi[2 * j + 1] >= 0 && (ai_ < 0 || cand[2 * j + 1] > am)) { am = cand[2 * j + 1]; ai_ = candi[2 * j + 1]; }
+        }
+        if (di_ >= 0 || ai_ >= 0) res |= 4;
+        WR_SYNC();
+        WR_Q_BEGIN
+        (void)t;
+        if (q == 0) { sh->flag[4] = di_; sh->flag[5] = di_ >= 0 ? -1 : ai_; }
+        WR_Q_END
+    }
     WR_SYNC();
     return res;
 }
 
-// A robot whose working set has settled: mark it for the finish kernel.
-CMPC_HD void mark_pending(int qlane, bool conv, TS* ts, const Env& e, int nst, int sweeps) {
+// Single exchange: next = cur with one row dropped (most negative multiplier) or, if there is none, one row added (most
+// violated), as left in sh->flag[4..5] by the forward sweep.
+CMPC_HD void single_step(int qlane, bool doit, TS* ts, Sh* sh, const unsigned char* cur, unsigned char* next, int N) {
     WR_Q_BEGIN
     (void)t;
-    if (conv && q == 0) {
-        e.bt->status[e.b] = ST_PENDING;
-        double* st = out_stats(e);
-        st[3] = (double)(3 * nst);
-        st[6] = (double)(sweeps - 1);
+    if (doit) for (int i = q; i < 4 * N; i += 4) next[i] = cur[i];
+    WR_Q_END
+    WR_SYNC();
+    WR_Q_BEGIN
+    (void)t;
+    if (doit && q == 0) {
+        const int drop = sh->flag[4], add = sh->flag[5];
+        const int idx = drop >= 0 ? drop : add;
+        if (idx >= 0) {
+            const int pos = idx / 5, r5 = idx - 5 * pos;
+            int c = next[pos];
+            const int on = drop >= 0 ? 0 : 1;
+            if (r5 == 0) c = on ? (c | 1) : (c & ~1);
+            else if (r5 <= 2) c = (c & ~(3 << 1)) | ((on ? r5 : 0) << 1);
+            else c = (c & ~(3 << 3)) | ((on ? r5 - 2 : 0) << 3);
+            next[pos] = (unsigned char)c;
+        }
     }
     WR_Q_END
+    WR_SYNC();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Finish (its own kernel, one quad per robot at full occupancy): co-states, stationarity and feasibility from first
-// principles -- X, u, y as written by the forward sweep, independent of the factorizations -- and the remaining outputs
-// in the reference's layouts.  Returns 1 if the certificate holds (status / statistics written), else 0.
+// Finish of a robot whose working set has settled: co-states, stationarity and feasibility from first principles -- X,
+// u, y as written by the forward sweep, independent of the factorizations -- and the remaining outputs in the
+// reference's layouts.  The inputs of a stage are prefetched two slots deep into the storage of PK.  Returns 1 if the
+// certificate holds (status / statistics written), else 0.
 // ------------------------------------------------------------------------------------------------------------------
-CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, int warm) {
+CMPC_HD void fin_issue(int q, bool valid, Sh* sh, int slot, const Env& e, int k) {
+    if (!valid) return;
+    const int N = e.bt->N;
+    double* d = sh->PK + slot * 72 + q * 18;
+    const double* xk = out_X(e) + 12 * k + 3 * q;
+    const double* xr = in_xref(e);
+    const double* rf = in_rfoot(e);
+    const double* f = out_u(e) + 12 * k + 3 * q;
+    const double* yo = out_y(e);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        cp8(d + c, xk + c);
+        cp8(d + 3 + c, xr + (size_t)(3 * q + c) * N + k);
+        cp8(d + 6 + c, rf + (size_t)(3 * q + c) * N + k);
+        cp8(d + 9 + c, f + c);
+    }
+    cp8(d + 12, yo + 12 * k + 3 * q + 2);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cp8(d + 13 + c, yo + 12 * N + 16 * k + 4 * q + c);
+}
+
+CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int warm, int nst, int sweeps) {
     const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
     const double dt = e.dt, h = e.h;
-    double* nus = sf->nus;
+    double* nus = sh->E3;
     WR_Q_BEGIN
-    if (valid && q == 0) robot_consts(e, sf->cst);
     t.red[0] = 0.0; t.red[1] = 0.0; t.red[2] = 0.0; t.red[3] = 0.0;       // rd, rp, objective part, active rows
     t.ax[0] = 0.0; t.ax[1] = 0.0; t.ax[2] = 0.0;                          // co-state block
     nus[3 * q] = 0.0; nus[3 * q + 1] = 0.0; nus[3 * q + 2] = 0.0;
+    fin_issue(q, valid, sh, (N - 1) & 1, e, N - 1);
     WR_Q_END
-    WR_SYNC();
     for (int k = N - 1; k >= 0; --k) {
         WR_Q_BEGIN
+        cp_commit_wait();
+        WR_Q_END
+        WR_SYNC();
+        WR_Q_BEGIN
+        if (k > 0) fin_issue(q, valid, sh, (k - 1) & 1, e, k - 1);
+        const double* d = sh->PK + (k & 1) * 72 + q * 18;
         const double dtc = (q >= 2 && k < N - 1) ? dt : 0.0;
-        const double rc = q == 3 ? sf->cst[0] : 1.0, rs = q == 3 ? sf->cst[1] : 0.0;
+        const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
         const double* X = nus + 3 * (q & 1);
         double s[3];
         s[0] = dtc * (rc * X[0] - rs * X[1]);
         s[1] = dtc * (rs * X[0] + rc * X[1]);
         s[2] = dtc * X[2];
-        if (valid) {
-            const double* xk = out_X(e) + 12 * k + 3 * q;
-            const double* xrp = in_xref(e);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double xr = xrp[(size_t)(3 * q + i) * N + k];
-                const double dd = xk[i] - xr;
-                s[i] += (k < N - 1 ? t.ax[i] : 0.0) - 2.0 * tb.Q[3 * q + i] * dd;
-                t.red[2] += tb.Q[3 * q + i] * (dd * dd - xr * xr);
-            }
+        for (int i = 0; i < 3; ++i) {
+            const double xr = d[3 + i];
+            const double dd = d[i] - xr;
+            s[i] += (k < N - 1 ? t.ax[i] : 0.0) - 2.0 * tb.Q[3 * q + i] * dd;
+            t.red[2] += tb.Q[3 * q + i] * (dd * dd - xr * xr);
         }
         t.qa[0] = s[0]; t.qa[1] = s[1]; t.qa[2] = s[2];
         WR_Q_END
@@ -782,20 +862,18 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, i
         WR_SYNC();
         WR_Q_BEGIN
         if (valid) {
+            const double* d = sh->PK + (k & 1) * 72 + q * 18;
             double bn[6];
-            bbar_t(sf->cst, dt, h, nus, bn);
-            double r[3], W[9], s3[3];
-            const double* rf = in_rfoot(e);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) r[c] = rf[(size_t)(3 * q + c) * N + k];
-            foot_W(sf->cst + 3, r, W);
+            bbar_t(sh->cst, dt, h, nus, bn);
+            double W[9], s3[3];
+            foot_W(sh->cst + 3, d + 6, W);
 #pragma unroll
             for (int c = 0; c < 3; ++c) s3[c] = bn[c] + W[c] * bn[3] + W[3 + c] * bn[4] + W[6 + c] * bn[5];
             double* yo = out_y(e);
             if (stance_at(e, q, k)) {
-                const double* f = out_u(e) + 12 * k + 3 * q;
-                const double* yf = yo + 12 * N + 16 * k + 4 * q;
-                const double l0 = -yo[12 * k + 3 * q + 2];
+                const double* f = d + 9;
+                const double* yf = d + 13;
+                const double l0 = -d[12];
                 const double atl[3] = {yf[0] - yf[1], yf[2] - yf[3], -l0 - p.mu * (yf[0] + yf[1] + yf[2] + yf[3])};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -816,14 +894,14 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, i
             }
         }
         WR_Q_END
-        WR_SYNC();
     }
+    WR_SYNC();
+    double* R4 = sh->FL;
     WR_Q_BEGIN
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sf->red[4 * q + i] = t.red[i];
+    for (int i = 0; i < 4; ++i) R4[4 * q + i] = t.red[i];
     WR_Q_END
     WR_SYNC();
-    const double* R4 = sf->red;
     const double rd = fmax(fmax(R4[0], R4[4]), fmax(R4[8], R4[12]));
     const double rp = fmax(fmax(R4[1], R4[5]), fmax(R4[9], R4[13]));
     const double obj = R4[2] + R4[6] + R4[10] + R4[14];
@@ -836,14 +914,15 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, i
         const double rho = (warm && rho_p && *rho_p > 0.0) ? *rho_p : p.rho0;
         if (rho_p) *rho_p = rho;
         double* st = out_stats(e);
-        const int sweeps = (int)st[6] + 1;
         e.bt->status[e.b] = ST_SOLVED;
         e.bt->iters[e.b] = 0;
         st[0] = fmax(rp, 0.0);
         st[1] = rd;
         st[2] = obj;
+        st[3] = (double)(3 * nst);
         st[4] = na;
         st[5] = rho;
+        st[6] = (double)(sweeps - 1);
         st[7] = (double)(sweeps > 1 ? (int)PATH_WRENCH : (int)PATH_RICCATI);
     }
     WR_Q_END
@@ -851,16 +930,19 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, ShF* sf, const Env& e, i
     return ok;
 }
 
-// One robot from set-up to outputs (host emulation; the device kernels in cmpc.cu interleave these steps over the
+constexpr int kSingleMax = 160;      // sweeps of the single-exchange phase before the robot is handed to the condensed kernel
+
+// One robot from set-up to outputs (host emulation; the device kernel in cmpc.cu interleaves these steps over the
 // eight robots of a warp).  Returns 1 if finished here, 0 if the robot goes on to the condensed kernel.
-CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, ShF* sf, const Env& e, int nfmax, int warm, int* sweeps_out) {
+CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int warm, int* sweeps_out) {
     const int N = e.bt->N;
     unsigned char* codes = codes_of(sh);
     const int nst = init_robot(qlane, true, ts, sh, e, warm);
     if (sweeps_out) *sweeps_out = 0;
     if (nst == 0 || nst > nfmax) return 0;
     const int max_it = e.p->pdas_max_iter;
-    for (int it = 0; it < max_it; ++it) {
+    bool single = false;
+    for (int it = 0; it < max_it + kSingleMax; ++it) {
         const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
         unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
         const unsigned char* prev = codes + (size_t)((it + 2) % 3) * 4 * N;
@@ -868,11 +950,10 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, ShF* sf, const Env& e, int nf
         if (!(pmin > 0.0)) return 0;
         const int fl = forward_sweep(qlane, true, ts, sh, e, cur, prev, next);
         if (sweeps_out) *sweeps_out = it + 1;
-        if (!(fl & 1)) {
-            mark_pending(qlane, true, ts, e, nst, it + 1);
-            return finish_robot(qlane, true, ts, sf, e, warm);
-        }
-        if (fl & 2) return 0;           // the new set is the one before: a 2-cycle
+        if (!single && (fl & 1) && ((fl & 2) || it + 1 >= max_it)) single = true;      // a 2-cycle or the budget: one row at a time
+        const bool conv = single ? !(fl & 4) : !(fl & 1);
+        if (conv) return finish_robot(qlane, true, ts, sh, e, warm, nst, it + 1);
+        single_step(qlane, single, ts, sh, cur, next, N);
     }
     return 0;
 }

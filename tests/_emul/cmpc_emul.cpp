@@ -192,7 +192,6 @@ int emul_wrench(const Params* p, int B, int N, int nfmax, const double* x0, cons
     wr::Tab tb;
     for (int i = 0; i < 16; ++i) wr::fill_tab(tb, *p, i);
     wr::TS ts[4];
-    wr::ShF sf;
     std::vector<double> xs((size_t)B * 12 * N);
     wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : xs.data(), nu, stats, status, iters, dt, N, (4 * N + 63) / 64};
     for (int b = 0; b < B; ++b) {
@@ -202,7 +201,7 @@ int emul_wrench(const Params* p, int B, int N, int nfmax, const double* x0, cons
         e.gstride = 4;
         e.dt = dt; e.h = dt * dt / 2.0;
         int sw = 0;
-        done[b] = wr::solve_robot(0, ts, sh, &sf, e, nfmax, warm, &sw);
+        done[b] = wr::solve_robot(0, ts, sh, e, nfmax, warm, &sw);
         sweeps[b] = sw;
     }
     return 0;

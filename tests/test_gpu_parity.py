@@ -292,7 +292,7 @@ def test_riccati_prepass_longer_horizons(mod, N):
     B = 2048
     rec = records.random_records(B, N=N, seed=700 + N, stress=0.2)
     ms = 4 * (int(np.floor(rec.duty * N)) + 1)
-    a, traj = make_mpc(mod, rec, max_stance=ms)                  # default: pre-pass on from 2 048 robots
+    a, traj = make_mpc(mod, rec, max_stance=ms, prepass=3)       # the lock-step sweep of round 1 (the default is now 4)
     b, _ = make_mpc(mod, rec, max_stance=ms, prepass=0)
     sa, sb = a.solve_QP(None, traj), b.solve_QP(None, traj)
     sta, stb = sa["stats"].cpu().numpy(), sb["stats"].cpu().numpy()

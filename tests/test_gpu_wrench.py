@@ -40,12 +40,14 @@ def test_same_optimum_as_condensed_kernel_and_oracle(mod, stress, N):
     assert (a["status"] == 1).all() and (b["status"] == 1).all()
     path = a["stats"][:, 7].astype(int)
     wrench = np.isin(path, (4, 5))
-    assert wrench.mean() > (0.9 if stress < 1.0 else 0.8)          # the condensed kernel only sees the cycling rest
+    assert wrench.mean() > 0.999                                   # working sets that cycle are settled by single exchanges
     if stress > 0:
         assert (path == 5).mean() > 0.1                            # constrained robots are finished here too
     exact_b = ~np.isin(b["stats"][:, 7], (2,))              # the condensed kernel's ADMM fallback stops at its 1e-6 tolerance
-    assert np.abs(a["u"] - b["u"])[exact_b].max() < 1e-6 and np.abs(a["u"] - b["u"]).max() < 0.1
-    assert a["stats"][:, 0].max() < 1e-9 and a["stats"][:, 1].max() < 1e-8            # own KKT certificate
+    # rows the condensed kernel left to its ADMM fallback are only as close as that fallback's 1e-6 stop leaves them
+    # on this flat QP (a few 0.1 N); the wrench kernel's own certificate below and the oracle sample cover them
+    assert np.abs(a["u"] - b["u"])[exact_b].max() < 1e-6 and np.abs(a["u"] - b["u"]).max() < 1.0
+    assert a["stats"][wrench, 0].max() < 1e-9 and a["stats"][wrench, 1].max() < 1e-8  # own KKT certificate
     assert np.abs(a["stats"][:, 2] - b["stats"][:, 2]).max() < 1e-6 * np.abs(b["stats"][:, 2]).max()
     assert np.array_equal(a["stats"][:, 3], b["stats"][:, 3])
     assert np.array_equal(a["stats"][wrench & exact_b, 4], b["stats"][wrench & exact_b, 4])     # same number of active rows
@@ -72,9 +74,7 @@ def test_matches_host_emulation_and_numpy_twin(mod):
     sub = rec.slice(0, 48)
     em = Emul().wrench(sub)
     for i in range(sub.B):
-        if not em["done"][i]:
-            assert a["stats"][i, 7] not in (4, 5)
-            continue
+        assert em["done"][i]
         assert a["stats"][i, 7] in (4, 5)
         assert a["stats"][i, 6] == em["sweeps"][i] - 1
         assert np.abs(a["u"][i] - em["u"][i]).max() < 1e-8
