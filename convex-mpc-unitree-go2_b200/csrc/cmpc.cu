@@ -350,7 +350,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         const bool conv = valid && !fail && (single ? !(fl & 4) : !(fl & 1));
         if (valid && !conv && it + 1 >= max_it + wr::kSingleMax) fail = true;
         if (__any_sync(0xffffffffu, conv)) {
-            const int ok = wr::finish_robot(qlane, conv, ts, sh, e, warm, nst, it + 1);
+            const int ok = wr::finish_robot(qlane, conv, ts, sh, e, cur, warm, nst, it + 1);
             if (conv && !ok) fail = true;
         }
         wr::single_step(qlane, single && valid && !conv && !fail, ts, sh, cur, next, N);
@@ -951,7 +951,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 // cannot finish (cycling working sets) goes to the condensed kernel through the work-list
                 const size_t smem_w = wrench_smem(h);
                 const int grid_w = wrench_grid(h, B);
-                if (smem_w <= h->smem_optin && (size_t)grid_w * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2) <= sl.gain_bytes) {
+                if ((h->N & 3) == 0 && smem_w <= h->smem_optin && (size_t)grid_w * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2) <= sl.gain_bytes) {
                     if (set_smem((const void*)wrench_pdas_kernel, smem_w, &h->attr_wrench)) return -1;
                     wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W};
                     wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bt, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),

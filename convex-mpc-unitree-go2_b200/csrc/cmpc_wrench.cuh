@@ -70,17 +70,19 @@ struct Tab {
 
 // shared memory of one robot (sweep kernel)
 struct Sh {
-    double E1[72];           // backward: (P Bbar) blocks [a][i][c]; forward: x (12) | mu partials (24) | wrench partials (24)
-    double E3[12];           // backward: p
-    double FL[4 * 28];       // backward: contribution of foot j to Lam_k (21) and what_k (6)
+    double E1[72];           // backward: S = P Bbar, [row 12][6]; forward: x (12) | mu partials (24) | wrench partials (24) | candidates
+    double E3[12];           // backward: p ; finish: co-state
     double D4[8];            // backward: d of the threads p, rpy
-    double PK[4 * 36];       // backward: the block rows of P while the 6 x 6 work needs the registers; finish: prefetched
-                             // inputs of a stage, 2 slots x 4 threads x 18 (x 3, xref 3, lever arm 3, force 3, duals 5)
+    double PK[4 * 36];       // backward: the block rows of P while the 6 x 6 work needs the registers, then the rows D A of the
+                             // threads p, rpy for their partners v, omega; finish: prefetched inputs of a stage, 2 slots x 4 threads x 18
+                             // (x 3, xref 3, lever arm 3, force 3, duals 5)
     double cst[12];          // cy, sy, 1/m, Iinv[9]
-    double ring[2][12];      // lever arms of a stage, prefetched
+    double ring[2][48];      // lever arms of four consecutive stages, [row 12][stage 4], prefetched a group ahead
     int flag[8];             // [0..3] per-thread PDAS flags; [4] row to drop, [5] row to add (single exchange), -1 = none
 };
-CMPC_HD size_t robot_bytes(int N) { return (sizeof(Sh) + (size_t)3 * 4 * N + 15) & ~(size_t)15; }
+// An odd number of 16-byte units: the eight robots of a warp then start in eight different bank groups, so a 16-byte
+// (or 8-byte) access at the same offset of every robot -- the broadcast reads of the 6 x 6 work -- is one wavefront.
+CMPC_HD size_t robot_bytes(int N) { return ((sizeof(Sh) + (size_t)3 * 4 * N + 15) & ~(size_t)15) | (size_t)16; }
 CMPC_HD unsigned char* codes_of(Sh* sh) { return reinterpret_cast<unsigned char*>(sh) + sizeof(Sh); }
 
 // per-thread state that lives across synchronisation points
@@ -88,6 +90,7 @@ struct TS {
     double P[36];            // block row a of P, P[i*12 + c] (registers between phase 3 and phase 1; parked in Sh::PK otherwise)
     double pv[3];            // block a of p ; forward: block a of x
     double qa[3];            // d_a
+    double pg[3];            // backward: block a of P g
     double xr[3];            // reference entries of the stage (own rows)
     double ax[3];            // forward: block a of A x_k ; finish: co-state block
     double red[4];           // finish: partial reductions
@@ -119,6 +122,14 @@ CMPC_HD void cp8(double* dst_smem, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 #else
     *dst_smem = *src;
+#endif
+}
+CMPC_HD void cp16(double* dst_smem, const double* src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+#else
+    dst_smem[0] = src[0]; dst_smem[1] = src[1];
 #endif
 }
 CMPC_HD void cp_commit_wait() {
@@ -278,13 +289,19 @@ CMPC_HD void bbar_t(const double* cst, double dt, double h, const double* v, dou
     out[5] = h * v[5] + dt * v[11];
 }
 
-// prefetch the lever arms of step kr
-CMPC_HD void ring_issue(int q, Sh* sh, int slot, const Env& e, int kr) {
+// prefetch the lever arms of the four stages of group g (stages 4g .. 4g+3; N is a multiple of 4): thread q brings the
+// three rows of foot q, 32 bytes = one sector each
+CMPC_HD void ring_issue(int q, Sh* sh, const Env& e, int g) {
     const int N = e.bt->N;
-    const double* rf = in_rfoot(e);
+    const double* rf = in_rfoot(e) + 4 * g;
+    double* dst = sh->ring[g & 1];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) cp8(&sh->ring[slot][3 * q + c], rf + (size_t)(3 * q + c) * N + kr);
+    for (int c = 0; c < 3; ++c) {
+        cp16(dst + (3 * q + c) * 4, rf + (size_t)(3 * q + c) * N);
+        cp16(dst + (3 * q + c) * 4 + 2, rf + (size_t)(3 * q + c) * N + 2);
+    }
 }
+CMPC_HD const double* ring_at(const Sh* sh, int k) { return sh->ring[(k >> 2) & 1] + (k & 3); }      // row r at [4 r]
 
 CMPC_HD void robot_consts(const Env& e, double* cst) {
     DynCommon dc;
@@ -331,6 +348,11 @@ CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int 
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward sweep for the working set cur.  Returns the smallest pivot seen (<= 0: not positive definite).
+//
+// What bounds this kernel is the load/store data pipe of the SM (shared-memory wavefronts), not the FP64 pipe, so a
+// stage moves as little as possible through shared memory: the per-foot terms of Lam_k are formed by every thread
+// itself (no exchange), S = P Bbar is read once for the 6 x 6 work and once for the update of all three rows, P is
+// parked once around the 6 x 6 work, and after the update only the rows the partner threads need are exchanged.
 // ------------------------------------------------------------------------------------------------------------------
 CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const unsigned char* cur) {
     const int N = e.bt->N;
@@ -347,60 +369,31 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         for (int c = 0; c < 12; ++c) t.P[i * 12 + c] = (c == 3 * q + i) ? tb.Q[3 * q + i] : 0.0;
         t.pv[i] = -tb.Q[3 * q + i] * xr[(size_t)(3 * q + i) * N + (N - 1)];
     }
-    ring_issue(q, sh, (N - 1) & 1, e, N - 1);
+    ring_issue(q, sh, e, (N - 1) >> 2);
     WR_Q_END
     for (int k = N - 1; k >= 0; --k) {
-        const double* ring = sh->ring[k & 1];
+        // ---- phase 1: own rows of S = P Bbar, P g, p_a; P is parked
         WR_Q_BEGIN
-        (void)t; (void)q;
-        cp_commit_wait();
-        WR_Q_END
-        WR_SYNC();
-        // ---- phase 1: foot q's contribution to Lam_k / what_k, own rows of P Bbar, p_a; P is parked
-        WR_Q_BEGIN
+        if ((k & 3) == 3 || k == N - 1) cp_commit_wait();             // the group of this stage has arrived (own copies)
         if (k > 0) {
-            ring_issue(q, sh, (k - 1) & 1, e, k - 1);
             const double* xr = in_xref(e);
 #pragma unroll
             for (int i = 0; i < 3; ++i) t.xr[i] = xr[(size_t)(3 * q + i) * N + (k - 1)];
         }
         const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
-        {
-            const FootP f = foot_proj(cur[4 * k + q], q, tb, p.mu, p.fz_min);
-            double W[9], Wz[3];
-            foot_W(sh->cst + 3, ring + 3 * q, W);
-#pragma unroll
-            for (int m = 0; m < 3; ++m) Wz[m] = W[m * 3] * f.zx + W[m * 3 + 1] * f.zy + W[m * 3 + 2];
-            const double sx = f.sg * f.zx, sy_ = f.sg * f.zy;
-            double* o = sh->FL + q * 28;
-            o[lt(0, 0)] = f.dx + sx * f.zx;
-            o[lt(1, 0)] = sx * f.zy;
-            o[lt(1, 1)] = f.dy + sy_ * f.zy;
-            o[lt(2, 0)] = sx;
-            o[lt(2, 1)] = sy_;
-            o[lt(2, 2)] = f.sg;
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const double a0 = f.dx * W[m * 3], a1 = f.dy * W[m * 3 + 1], a2 = f.sg * Wz[m];
-                o[lt(3 + m, 0)] = a0 + sx * Wz[m];
-                o[lt(3 + m, 1)] = a1 + sy_ * Wz[m];
-                o[lt(3 + m, 2)] = a2;
-#pragma unroll
-                for (int n = 0; n <= m; ++n) o[lt(3 + m, 3 + n)] = a0 * W[n * 3] + a1 * W[n * 3 + 1] + a2 * Wz[n];
-            }
-            o[21] = f.fh * f.zx; o[22] = f.fh * f.zy; o[23] = f.fh;
-#pragma unroll
-            for (int m = 0; m < 3; ++m) o[24 + m] = f.fh * Wz[m];
-        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double* Pi = t.P + i * 12;
             double* o = sh->E1 + q * 18 + i * 6;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) o[c] = minv * (h * Pi[c] + dt * Pi[6 + c]);
-            o[3] = h * (Pi[3] * cy - Pi[4] * sy) + dt * Pi[9];
-            o[4] = h * (Pi[3] * sy + Pi[4] * cy) + dt * Pi[10];
-            o[5] = h * Pi[5] + dt * Pi[11];
+            D2 v0, v1, v2;
+            v0.x = minv * (h * Pi[0] + dt * Pi[6]);
+            v0.y = minv * (h * Pi[1] + dt * Pi[7]);
+            v1.x = minv * (h * Pi[2] + dt * Pi[8]);
+            v1.y = h * (Pi[3] * cy - Pi[4] * sy) + dt * Pi[9];
+            v2.x = h * (Pi[3] * sy + Pi[4] * cy) + dt * Pi[10];
+            v2.y = h * Pi[5] + dt * Pi[11];
+            *reinterpret_cast<D2*>(o) = v0; *reinterpret_cast<D2*>(o + 2) = v1; *reinterpret_cast<D2*>(o + 4) = v2;
+            t.pg[i] = -9.81 * (h * Pi[2] + dt * Pi[8]);
             sh->E3[3 * q + i] = t.pv[i];
             if (k > 0) {
                 double* pk = sh->PK + q * 36 + i * 12;
@@ -410,47 +403,55 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         }
         WR_Q_END
         WR_SYNC();
-        // ---- phase 2: 6 x 6 factorizations (every thread), vector part, gains, own rows of D = P - (P Bbar) Phi (P Bbar)' and D A
+        // ---- phase 2: Lam_k / what_k from the four feet, 6 x 6 factorizations (every thread), vector part, gains, own rows of
+        //      D = P - S Phi S' and of D A
         WR_Q_BEGIN
+        if ((k & 3) == 3 && k >= 4) ring_issue(q, sh, e, (k >> 2) - 1);      // next group (every thread of the quad has passed the wait above)
         const double cy = sh->cst[0], sy = sh->cst[1], minv = sh->cst[2];
         const double* E1 = sh->E1;
         const double* own = E1 + q * 18;
-        double lam[21], bq[6];
-        {   // Lam_k and what_k from the four feet; ghat; q_a = P_a ghat + p_a; bq = Bbar'q = (P Bbar)' ghat + Bbar' p
-            double wh[6], gh[12];
-            const double* F = sh->FL;
+        double lam[21], wh[6], bq[6];
+        {
 #pragma unroll
-            for (int i = 0; i < 20; i += 2) {
-                const D2 a = ld2(F + i), b = ld2(F + 28 + i), c = ld2(F + 56 + i), d = ld2(F + 84 + i);
-                lam[i] = (a.x + b.x) + (c.x + d.x);
-                lam[i + 1] = (a.y + b.y) + (c.y + d.y);
-            }
-            {
-                const D2 a = ld2(F + 20), b = ld2(F + 28 + 20), c = ld2(F + 56 + 20), d = ld2(F + 84 + 20);
-                lam[20] = (a.x + b.x) + (c.x + d.x);
-                wh[0] = (a.y + b.y) + (c.y + d.y);
-            }
+            for (int i = 0; i < 21; ++i) lam[i] = 0.0;
 #pragma unroll
-            for (int i = 22; i < 26; i += 2) {
-                const D2 a = ld2(F + i), b = ld2(F + 28 + i), c = ld2(F + 56 + i), d = ld2(F + 84 + i);
-                wh[i - 21] = (a.x + b.x) + (c.x + d.x);
-                wh[i - 20] = (a.y + b.y) + (c.y + d.y);
+            for (int i = 0; i < 6; ++i) wh[i] = 0.0;
+            const double* rg = ring_at(sh, k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const FootP f = foot_proj(cur[4 * k + j], j, tb, p.mu, p.fz_min);
+                const double r3[3] = {rg[(3 * j) * 4], rg[(3 * j + 1) * 4], rg[(3 * j + 2) * 4]};
+                double W[9], Wz[3];
+                foot_W(sh->cst + 3, r3, W);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) Wz[m] = W[m * 3] * f.zx + W[m * 3 + 1] * f.zy + W[m * 3 + 2];
+                const double sx = f.sg * f.zx, sy_ = f.sg * f.zy;
+                lam[lt(0, 0)] += f.dx + sx * f.zx;
+                lam[lt(1, 0)] += sx * f.zy;
+                lam[lt(1, 1)] += f.dy + sy_ * f.zy;
+                lam[lt(2, 0)] += sx;
+                lam[lt(2, 1)] += sy_;
+                lam[lt(2, 2)] += f.sg;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const double a0 = f.dx * W[m * 3], a1 = f.dy * W[m * 3 + 1], a2 = f.sg * Wz[m];
+                    lam[lt(3 + m, 0)] += a0 + sx * Wz[m];
+                    lam[lt(3 + m, 1)] += a1 + sy_ * Wz[m];
+                    lam[lt(3 + m, 2)] += a2;
+#pragma unroll
+                    for (int n = 0; n <= m; ++n) lam[lt(3 + m, 3 + n)] += a0 * W[n * 3] + a1 * W[n * 3 + 1] + a2 * Wz[n];
+                }
+                wh[0] += f.fh * f.zx; wh[1] += f.fh * f.zy; wh[2] += f.fh;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) wh[3 + m] += f.fh * Wz[m];
             }
-            wh[5] = (F[26] + F[28 + 26]) + (F[56 + 26] + F[84 + 26]);
+        }
+        {   // ghat = g + Bbar what;  bq = Bbar'q = S' ghat + Bbar' p
+            double gh[12];
 #pragma unroll
             for (int a = 0; a < 4; ++a) bbar_rows(a, sh->cst, dt, h, wh, gh + 3 * a);
             gh[2] += -9.81 * h;
             gh[8] += -9.81 * dt;
-            if (k > 0) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double* pk = sh->PK + q * 36 + i * 12;
-                    double d = t.pv[i];
-#pragma unroll
-                    for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); d += v.x * gh[c] + v.y * gh[c + 1]; }
-                    t.qa[i] = d;
-                }
-            }
             bbar_t(sh->cst, dt, h, sh->E3, bq);
 #pragma unroll
             for (int r = 0; r < 12; ++r) {
@@ -460,7 +461,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
             }
         }
         double L[21], di[6];
-        {   // Gbar = Bbar' (P Bbar), lower triangle
+        {   // Gbar = Bbar' S, lower triangle
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -486,10 +487,10 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         nn_col<3>(lam, L, Ln); nn_col<4>(lam, L, Ln); nn_col<5>(lam, L, Ln);
         chol6(Ln, dn);
         D2* g = e.gains + WR_GQ + (size_t)k * GAIN_D2 * e.gstride;
-        // vector part: kbar = Gam bq,  phiq = Phi bq
-        double phiq[6];
+        // vector part: kbar = Gam bq,  phiq = Phi bq;  dvec = what - phiq enters d_a = p_a + (P g)_a + S_a (what - Phi bq)
+        double dvec[6];
         {
-            double w[6], kb[6];
+            double w[6], kb[6], phiq[6];
             fsub6(L, di, bq);
 #pragma unroll
             for (int c = 0; c < 6; ++c) w[c] = bq[c];
@@ -499,12 +500,15 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 #pragma unroll
             for (int c = 0; c < 6; ++c) phiq[c] = bq[c] - w[c];
             bsub6(L, di, phiq);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dvec[c] = wh[c] - phiq[c];
             D2 kk;
             kk.x = q == 0 ? kb[0] : (q == 1 ? kb[2] : (q == 2 ? kb[4] : 0.0));
             kk.y = q == 0 ? kb[1] : (q == 1 ? kb[3] : (q == 2 ? kb[5] : 0.0));
             g[9 * e.gstride] = kk;
         }
-        // gains and the rows of D, one row at a time
+        // gains and z_i = Phi S_i', one row at a time
+        double z[18];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             double y[6], w[6], kt[6];
@@ -512,10 +516,10 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
                 const D2 a = ld2(own + i * 6), b = ld2(own + i * 6 + 2), c = ld2(own + i * 6 + 4);
                 y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y;
             }
-            if (k > 0) {      // d_a = q_a - (P Bbar)_a Phi bq
-                double d = t.qa[i];
+            if (k > 0) {      // d_a = p_a + (P g)_a + S_a (what - Phi bq)
+                double d = t.pv[i] + t.pg[i];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) d -= y[c] * phiq[c];
+                for (int c = 0; c < 6; ++c) d += y[c] * dvec[c];
                 t.qa[i] = d;
                 if (q < 2) sh->D4[q * 4 + i] = d;
             }
@@ -528,26 +532,36 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 #pragma unroll
             for (int c = 0; c < 3; ++c) { D2 v; v.x = kt[2 * c]; v.y = kt[2 * c + 1]; g[(3 * i + c) * e.gstride] = v; }
             if (k > 0) {
-                double z[6];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) z[c] = y[c] - w[c];
-                bsub6(L, di, z);
-                double* pk = sh->PK + q * 36 + i * 12;
-                double Pi[12];
+                for (int c = 0; c < 6; ++c) z[i * 6 + c] = y[c] - w[c];
+                bsub6(L, di, z + i * 6);
+            }
+        }
+        if (k > 0) {
+            // the three rows of D = P - Z S' together (S is read once), then D A; the rows of p, rpy go to their partners
+            double* pk = sh->PK + q * 36;
 #pragma unroll
-                for (int c = 0; c < 12; c += 2) { const D2 v = ld2(pk + c); Pi[c] = v.x; Pi[c + 1] = v.y; }
+            for (int c = 0; c < 36; c += 2) { const D2 v = ld2(pk + c); t.P[c] = v.x; t.P[c + 1] = v.y; }
 #pragma unroll
-                for (int b = 0; b < 12; ++b) {
-                    const D2 a = ld2(E1 + b * 6), bb = ld2(E1 + b * 6 + 2), c = ld2(E1 + b * 6 + 4);
-                    Pi[b] -= z[0] * a.x + z[1] * a.y + z[2] * bb.x + z[3] * bb.y + z[4] * c.x + z[5] * c.y;
+            for (int b = 0; b < 12; ++b) {
+                const D2 a = ld2(E1 + b * 6), bb = ld2(E1 + b * 6 + 2), c = ld2(E1 + b * 6 + 4);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double* zi = z + i * 6;
+                    t.P[i * 12 + b] -= zi[0] * a.x + zi[1] * a.y + zi[2] * bb.x + zi[3] * bb.y + zi[4] * c.x + zi[5] * c.y;
                 }
-                // D A (own row)
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double* Pi = t.P + i * 12;
                 Pi[6] += dt * Pi[0]; Pi[7] += dt * Pi[1]; Pi[8] += dt * Pi[2];
                 Pi[9] += dt * (cy * Pi[3] - sy * Pi[4]);
                 Pi[10] += dt * (sy * Pi[3] + cy * Pi[4]);
                 Pi[11] += dt * Pi[5];
+            }
+            if (q < 2) {
 #pragma unroll
-                for (int c = 0; c < 12; c += 2) { D2 v; v.x = Pi[c]; v.y = Pi[c + 1]; *reinterpret_cast<D2*>(pk + c) = v; }
+                for (int c = 0; c < 36; c += 2) { D2 v; v.x = t.P[c]; v.y = t.P[c + 1]; *reinterpret_cast<D2*>(pk + c) = v; }
             }
         }
         WR_Q_END
@@ -555,21 +569,27 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         WR_SYNC();
         // ---- phase 3: P <- Q + A'(D A),  p <- -Q xref + A' d
         WR_Q_BEGIN
+        const double q0 = tb.Q[3 * q], q1 = tb.Q[3 * q + 1], q2 = tb.Q[3 * q + 2];
         const double dtc = q >= 2 ? dt : 0.0;
         const double rc = q == 3 ? sh->cst[0] : 1.0, rs = q == 3 ? sh->cst[1] : 0.0;
-        const double* X = sh->PK + (q & 1) * 36;          // rows of the partner block (p for v, rpy for omega)
-        const double* O = sh->PK + q * 36;
-        const double q0 = tb.Q[3 * q], q1 = tb.Q[3 * q + 1], q2 = tb.Q[3 * q + 2];
+        if (q >= 2) {
+            const double* X = sh->PK + (q & 1) * 36;          // rows of the partner block (p for v, rpy for omega)
 #pragma unroll
-        for (int c = 0; c < 12; c += 2) {       // selects: P is a register array, its indices must be compile-time constants
-            const D2 x0 = ld2(X + c), x1 = ld2(X + 12 + c), x2 = ld2(X + 24 + c);
-            const D2 o0 = ld2(O + c), o1 = ld2(O + 12 + c), o2 = ld2(O + 24 + c);
-            t.P[c] = o0.x + dtc * (rc * x0.x - rs * x1.x) + ((c == 3 * q) ? q0 : 0.0);
-            t.P[c + 1] = o0.y + dtc * (rc * x0.y - rs * x1.y) + ((c + 1 == 3 * q) ? q0 : 0.0);
-            t.P[12 + c] = o1.x + dtc * (rs * x0.x + rc * x1.x) + ((c == 3 * q + 1) ? q1 : 0.0);
-            t.P[12 + c + 1] = o1.y + dtc * (rs * x0.y + rc * x1.y) + ((c + 1 == 3 * q + 1) ? q1 : 0.0);
-            t.P[24 + c] = o2.x + dtc * x2.x + ((c == 3 * q + 2) ? q2 : 0.0);
-            t.P[24 + c + 1] = o2.y + dtc * x2.y + ((c + 1 == 3 * q + 2) ? q2 : 0.0);
+            for (int c = 0; c < 12; c += 2) {
+                const D2 x0 = ld2(X + c), x1 = ld2(X + 12 + c), x2 = ld2(X + 24 + c);
+                t.P[c] += dt * (rc * x0.x - rs * x1.x);
+                t.P[c + 1] += dt * (rc * x0.y - rs * x1.y);
+                t.P[12 + c] += dt * (rs * x0.x + rc * x1.x);
+                t.P[12 + c + 1] += dt * (rs * x0.y + rc * x1.y);
+                t.P[24 + c] += dt * x2.x;
+                t.P[24 + c + 1] += dt * x2.y;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {       // selects: P is a register array, its indices must be compile-time constants
+            t.P[c] += (c == 3 * q) ? q0 : 0.0;
+            t.P[12 + c] += (c == 3 * q + 1) ? q1 : 0.0;
+            t.P[24 + c] += (c == 3 * q + 2) ? q2 : 0.0;
         }
         const double* D = sh->D4 + (q & 1) * 4;
         const double d0 = D[0], d1 = D[1], d2 = D[2];
@@ -577,6 +597,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
         t.pv[1] = t.qa[1] + dtc * (rs * d0 + rc * d1) - q1 * t.xr[1];
         t.pv[2] = t.qa[2] + dtc * d2 - q2 * t.xr[2];
         WR_Q_END
+        WR_SYNC();            // the partners' rows and S are rewritten in the next stage
     }
     WR_SYNC();
     return pmin;
@@ -598,33 +619,26 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     double* wp = sh->E1 + 36;
     WR_Q_BEGIN
     const double* x0 = e.bt->x0 + (size_t)e.b * 12;
-    const double* rf = in_rfoot(e);
 #pragma unroll
     for (int i = 0; i < 3; ++i) t.pv[i] = x0[3 * q + i];
     t.chg = 0; t.cyc = 1;
     t.dworst = -tol; t.amost = 1e-9; t.didx = -1; t.aidx = -1;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) cp8(&sh->ring[0][3 * q + c], rf + (size_t)(3 * q + c) * N);
+    ring_issue(q, sh, e, 0);
     const D2* g = e.gains + WR_GQ;
 #pragma unroll
     for (int i = 0; i < GAIN_D2; ++i) t.gk[i] = g[i * e.gstride];
     WR_Q_END
     for (int k = 0; k < N; ++k) {
-        double* ring = sh->ring[k & 1];
         // ---- F1: publish x
         WR_Q_BEGIN
-        cp_commit_wait();
+        if ((k & 3) == 0) cp_commit_wait();
 #pragma unroll
         for (int i = 0; i < 3; ++i) xs[3 * q + i] = t.pv[i];
         WR_Q_END
         WR_SYNC();
         // ---- F2: A x (own block), partial wrench co-state; gains of the next stage
         WR_Q_BEGIN
-        if (k + 1 < N) {
-            const double* rf = in_rfoot(e);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) cp8(&sh->ring[(k + 1) & 1][3 * q + c], rf + (size_t)(3 * q + c) * N + k + 1);
-        }
+        if ((k & 3) == 0 && k + 4 < N) ring_issue(q, sh, e, (k >> 2) + 1);
         const double dtf = q < 2 ? dt : 0.0;
         const double rc = q == 1 ? sh->cst[0] : 1.0, rs = q == 1 ? sh->cst[1] : 0.0;
         const double* X = xs + 3 * (q | 2);
@@ -660,7 +674,11 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         const unsigned char code = cur[4 * k + q];
         const FootP f = foot_proj(code, q, tb, p.mu, p.fz_min);
         double W[9];
-        foot_W(sh->cst + 3, ring + 3 * q, W);
+        {
+            const double* rg = ring_at(sh, k) + 12 * q;
+            const double r3[3] = {rg[0], rg[4], rg[8]};
+            foot_W(sh->cst + 3, r3, W);
+        }
         double tv[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) tv[c] = mu6[c] + W[c] * mu6[3] + W[3 + c] * mu6[4] + W[6 + c] * mu6[5];
@@ -814,7 +832,7 @@ CMPC_HD void fin_issue(int q, bool valid, Sh* sh, int slot, const Env& e, int k)
     for (int c = 0; c < 4; ++c) cp8(d + 13 + c, yo + 12 * N + 16 * k + 4 * q + c);
 }
 
-CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int warm, int nst, int sweeps) {
+CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur, int warm, int nst, int sweeps) {
     const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
@@ -870,7 +888,7 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, in
 #pragma unroll
             for (int c = 0; c < 3; ++c) s3[c] = bn[c] + W[c] * bn[3] + W[3 + c] * bn[4] + W[6 + c] * bn[5];
             double* yo = out_y(e);
-            if (stance_at(e, q, k)) {
+            if (cur[4 * k + q] != SWING) {
                 const double* f = d + 9;
                 const double* yf = d + 13;
                 const double l0 = -d[12];
@@ -896,7 +914,7 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, in
         WR_Q_END
     }
     WR_SYNC();
-    double* R4 = sh->FL;
+    double* R4 = sh->E1;
     WR_Q_BEGIN
 #pragma unroll
     for (int i = 0; i < 4; ++i) R4[4 * q + i] = t.red[i];
@@ -939,7 +957,7 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
     unsigned char* codes = codes_of(sh);
     const int nst = init_robot(qlane, true, ts, sh, e, warm);
     if (sweeps_out) *sweeps_out = 0;
-    if (nst == 0 || nst > nfmax) return 0;
+    if (nst == 0 || nst > nfmax || (N & 3)) return 0;     // lever arms are fetched four stages at a time
     const int max_it = e.p->pdas_max_iter;
     bool single = false;
     for (int it = 0; it < max_it + kSingleMax; ++it) {
@@ -952,7 +970,7 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
         if (sweeps_out) *sweeps_out = it + 1;
         if (!single && (fl & 1) && ((fl & 2) || it + 1 >= max_it)) single = true;      // a 2-cycle or the budget: one row at a time
         const bool conv = single ? !(fl & 4) : !(fl & 1);
-        if (conv) return finish_robot(qlane, true, ts, sh, e, warm, nst, it + 1);
+        if (conv) return finish_robot(qlane, true, ts, sh, e, cur, warm, nst, it + 1);
         single_step(qlane, single, ts, sh, cur, next, N);
     }
     return 0;
