@@ -79,6 +79,8 @@ struct Sh {
     double cst[12];          // cy, sy, 1/m, Iinv[9]
     double ring[2][48];      // lever arms of four consecutive stages, [row 12][stage 4], prefetched a group ahead
     int flag[8];             // [0..3] per-thread PDAS flags; [4] row to drop, [5] row to add (single exchange), -1 = none
+    unsigned hq[4];          // per-thread hash of the next working set
+    unsigned hist[8];        // hashes of the last eight working sets (cycle detection)
 };
 // An odd number of 16-byte units: the eight robots of a warp then start in eight different bank groups, so a 16-byte
 // (or 8-byte) access at the same offset of every robot -- the broadcast reads of the 6 x 6 work -- is one wavefront.
@@ -95,7 +97,8 @@ struct TS {
     double ax[3];            // forward: block a of A x_k ; finish: co-state block
     double red[4];           // finish: partial reductions
     D2 gk[GAIN_D2];          // forward: gains of the current stage (loaded one stage ahead)
-    int chg, cyc;
+    int chg;
+    unsigned hsh;            // forward: running hash of this thread's part of the next working set
     double dworst, amost;    // forward: single-exchange candidates of this thread's foot (most negative multiplier, largest violation)
     int didx, aidx;
 };
@@ -605,10 +608,15 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward sweep: states, forces, multipliers, next working set.  Writes forces / stance duals / states to the output
-// arrays when `valid`.  Returns bit 0: the working set changed, bit 1: the new set equals `prev` (a 2-cycle).
+// arrays when `valid`.  Returns bit 0: the working set changed, bit 1: the new set is one of the last eight (a cycle;
+// `it` = sweeps done before this one = valid entries of the history), bit 2: there is a single-exchange candidate,
+// bits 8 and up: the number of foot-steps whose working set changed.
 // ------------------------------------------------------------------------------------------------------------------
+// With `damp` the block update is one-sided on every other foot-step: rows whose multiplier is negative leave the working
+// set only where k + foot + it is even (violated rows always join).  Dropping half of the candidates per sweep is what
+// keeps the updates of heavily disturbed robots (40+ active rows) from oscillating; see policy_step.
 CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, const unsigned char* cur,
-                          const unsigned char* prev, unsigned char* next) {
+                          unsigned char* next, int it, bool damp) {
     const int N = e.bt->N;
     const Params& p = *e.p;
     const Tab& tb = *e.tb;
@@ -621,7 +629,7 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     const double* x0 = e.bt->x0 + (size_t)e.b * 12;
 #pragma unroll
     for (int i = 0; i < 3; ++i) t.pv[i] = x0[3 * q + i];
-    t.chg = 0; t.cyc = 1;
+    t.chg = 0; t.hsh = 2166136261u;
     t.dworst = -tol; t.amost = 1e-9; t.didx = -1; t.aidx = -1;
     ring_issue(q, sh, e, 0);
     const D2* g = e.gains + WR_GQ;
@@ -702,7 +710,9 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
             const int nz = s0 > tol;
             const int nx = (s1 > tol && s1 >= s2) ? 1 : ((s2 > tol && s2 > s1) ? 2 : 0);
             const int ny = (s3 > tol && s3 >= s4) ? 1 : ((s4 > tol && s4 > s3) ? 2 : 0);
-            nc = (unsigned char)(nz | (nx << 1) | (ny << 3));
+            const bool keep = damp && (((k + q + it) & 1) != 0);
+            const int nz2 = (keep && az) ? 1 : nz, nx2 = (keep && ax != 0) ? ax : nx, ny2 = (keep && ay != 0) ? ay : ny;
+            nc = (unsigned char)(nz2 | (nx2 << 1) | (ny2 << 3));
             // single-exchange candidates (solve_active_set_fast, second phase): the most negative multiplier of the
             // working set, the most violated row outside it (not the face opposite to an active one)
             const double vv[5] = {p.fz_min - fo[2], fo[0] - p.mu * fo[2], -fo[0] - p.mu * fo[2], fo[1] - p.mu * fo[2], -fo[1] - p.mu * fo[2]};
@@ -716,8 +726,8 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
             }
         }
         next[4 * k + q] = nc;
-        t.chg |= (nc != code);
-        t.cyc &= (nc == prev[4 * k + q]);
+        t.chg += (nc != code);
+        t.hsh = (t.hsh ^ nc) * 16777619u;
         if (valid) {
             double* uo = out_u(e) + 12 * k + 3 * q;
             double* yo = out_y(e);
@@ -753,13 +763,23 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     double* cand = sh->E1 + 60;           // 4 x (value of the drop candidate, value of the add candidate)
     int* candi = reinterpret_cast<int*>(sh->E1 + 68);
     WR_Q_BEGIN
-    sh->flag[q] = t.chg | (t.cyc << 1);
+    sh->flag[q] = t.chg;
+    sh->hq[q] = t.hsh;
     cand[2 * q] = t.dworst; cand[2 * q + 1] = t.amost;
     candi[2 * q] = t.didx; candi[2 * q + 1] = t.aidx;
     WR_Q_END
     WR_SYNC();
-    res = (sh->flag[0] | sh->flag[1] | sh->flag[2] | sh->flag[3]) & 1;
-    res |= (sh->flag[0] & sh->flag[1] & sh->flag[2] & sh->flag[3]) & 2;
+    const int nchg = sh->flag[0] + sh->flag[1] + sh->flag[2] + sh->flag[3];
+    res = (nchg > 0 ? 1 : 0) | (nchg << 8);
+    // (a damped update depends on the parity of the sweep, so the same set at the other parity is not a repetition)
+    const unsigned H = sh->hq[0] * 0x9E3779B1u + sh->hq[1] * 0x85EBCA77u + sh->hq[2] * 0xC2B2AE3Du + sh->hq[3] * 0x27D4EB2Fu +
+                       ((damp && (it & 1)) ? 0x165667B1u : 0u);
+    {
+        const int nh = it < 8 ? it : 8;
+        bool rep = false;
+        for (int j = 0; j < nh; ++j) rep |= (sh->hist[j] == H);
+        if (rep) res |= 2;
+    }
     {   // the same reduction in every thread: worst drop candidate, else best add candidate
         double dw = 0.0, am = 0.0;
         int di_ = -1, ai_ = -1;
@@ -771,7 +791,7 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         WR_SYNC();
         WR_Q_BEGIN
         (void)t;
-        if (q == 0) { sh->flag[4] = di_; sh->flag[5] = di_ >= 0 ? -1 : ai_; }
+        if (q == 0) { sh->flag[4] = di_; sh->flag[5] = di_ >= 0 ? -1 : ai_; sh->hist[it & 7] = H; }
         WR_Q_END
     }
     WR_SYNC();
@@ -948,7 +968,33 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, co
     return ok;
 }
 
-constexpr int kSingleMax = 160;      // sweeps of the single-exchange phase before the robot is handed to the condensed kernel
+constexpr int kSingleMax = 8;        // single exchanges after the block budget before the robot is handed to the condensed kernel
+constexpr int kBreakMax = 6;         // one-off single exchanges (cycle breakers) before the robot stays in single-exchange mode
+constexpr int kDampAfter = 8;        // block updates are one-sided on every other foot-step from this sweep on
+constexpr int kBlockExtra = 12;      // block updates: pdas_max_iter + kBlockExtra sweeps (damped updates of disturbed robots take up to ~20)
+
+// Working-set policy after a sweep (the same in the device kernel and in solve_robot).  Block updates by the primal-dual
+// rule settle the nominal robots in 1-6 sweeps; on heavily disturbed robots (40+ active rows) the plain rule oscillates,
+// so from sweep kDampAfter on the updates are damped (forward_sweep, `damp`) -- all sampled disturbed robots then settle in
+// 9-20 sweeps instead of not at all.  A working set that comes back (hash history, any period up to 8) is moved off the
+// cycle by ONE single exchange (most negative multiplier out, else most violated row in); after kBreakMax such breaks, or
+// when the block budget is spent, single exchanges only.
+// fl: flags of forward_sweep.  Returns 1 = converged, 0 = go on; `single` tells which update to apply.
+struct Policy { int nbreak; bool latched; };
+CMPC_HD bool policy_damp(int it) { return it >= kDampAfter; }
+CMPC_HD int policy_step(Policy& pl, int fl, int it, int max_it, bool& single) {
+    single = pl.latched;
+    if (pl.latched || policy_damp(it)) { if (!(fl & 4)) return 1; }      // nothing to exchange: the Karush-Kuhn-Tucker conditions hold
+    else if (!(fl & 1)) return 1;
+    if (pl.latched) return 0;
+    const bool budget = it + 1 >= max_it + kBlockExtra;
+    if (((fl & 1) && (fl & 2)) || budget) {
+        single = true;
+        if (++pl.nbreak > kBreakMax || budget) pl.latched = true;
+        if (!(fl & 4)) return 1;
+    }
+    return 0;
+}
 
 // One robot from set-up to outputs (host emulation; the device kernel in cmpc.cu interleaves these steps over the
 // eight robots of a warp).  Returns 1 if finished here, 0 if the robot goes on to the condensed kernel.
@@ -959,18 +1005,17 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
     if (sweeps_out) *sweeps_out = 0;
     if (nst == 0 || nst > nfmax || (N & 3)) return 0;     // lever arms are fetched four stages at a time
     const int max_it = e.p->pdas_max_iter;
-    bool single = false;
-    for (int it = 0; it < max_it + kSingleMax; ++it) {
+    Policy pl{0, false};
+    for (int it = 0; it < max_it + kBlockExtra + kSingleMax; ++it) {
         const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
         unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
-        const unsigned char* prev = codes + (size_t)((it + 2) % 3) * 4 * N;
         const double pmin = backward_sweep(qlane, ts, sh, e, cur);
         if (!(pmin > 0.0)) return 0;
-        const int fl = forward_sweep(qlane, true, ts, sh, e, cur, prev, next);
+        const int fl = forward_sweep(qlane, true, ts, sh, e, cur, next, it, policy_damp(it));
         if (sweeps_out) *sweeps_out = it + 1;
-        if (!single && (fl & 1) && ((fl & 2) || it + 1 >= max_it)) single = true;      // a 2-cycle or the budget: one row at a time
-        const bool conv = single ? !(fl & 4) : !(fl & 1);
-        if (conv) return finish_robot(qlane, true, ts, sh, e, cur, warm, nst, it + 1);
+        bool single;
+        const int ps = policy_step(pl, fl, it, max_it, single);
+        if (ps == 1) return finish_robot(qlane, true, ts, sh, e, cur, warm, nst, it + 1);
         single_step(qlane, single, ts, sh, cur, next, N);
     }
     return 0;

@@ -40,7 +40,9 @@ def test_same_optimum_as_condensed_kernel_and_oracle(mod, stress, N):
     assert (a["status"] == 1).all() and (b["status"] == 1).all()
     path = a["stats"][:, 7].astype(int)
     wrench = np.isin(path, (4, 5))
-    assert wrench.mean() > 0.999                                   # working sets that cycle are settled by single exchanges
+    # cycling working sets are moved off the cycle by single exchanges; only oscillating block updates of heavily
+    # disturbed robots (40+ active rows) and spent budgets go on to the condensed kernel
+    assert wrench.mean() > (0.999 if stress == 0 else (0.99 if stress < 1.0 else 0.95))
     if stress > 0:
         assert (path == 5).mean() > 0.1                            # constrained robots are finished here too
     exact_b = ~np.isin(b["stats"][:, 7], (2,))              # the condensed kernel's ADMM fallback stops at its 1e-6 tolerance
@@ -74,7 +76,9 @@ def test_matches_host_emulation_and_numpy_twin(mod):
     sub = rec.slice(0, 48)
     em = Emul().wrench(sub)
     for i in range(sub.B):
-        assert em["done"][i]
+        if not em["done"][i]:
+            assert a["stats"][i, 7] not in (4, 5)
+            continue
         assert a["stats"][i, 7] in (4, 5)
         assert a["stats"][i, 6] == em["sweeps"][i] - 1
         assert np.abs(a["u"][i] - em["u"][i]).max() < 1e-8
