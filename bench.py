@@ -42,7 +42,7 @@ WORKLOAD = "BASELINE configs[2]: 65536 randomized Go2 states+references per GPU,
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=500, help="timed steps (default 500: about 2 s of device time per arm)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="robots per GPU")
@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--stress", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--prepass", type=int, default=3, help="Riccati pre-pass ahead of the condensed kernel: 0 off, 1 v1, 2 v2, 3 v2 lock-step (default)")
+    ap.add_argument("--prepass", type=int, default=4, help="kernel ahead of the condensed kernel: 0 off, 1-3 Riccati sweeps of round 1 (nominal robots only), "
+                                                           "4 wrench-space projected-Riccati active set for all robots (default)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep 1..262144 -> gpurun_out/sweep.json")
     return ap.parse_args()
 
@@ -59,17 +60,55 @@ def parse():
 # clocks during the timed region (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU while the timed region runs: NVML polled from a thread every 5 ms
+    (nvidia_ml_py), else ``nvidia-smi -lms 20``."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.stop_flag, self.nvml = [], False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        R = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = get_reasons(self.h)
+                self.samples.append((float(sm), float(mx), pw, {k for k, bit in R.items() if rs & bit}))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,33 +120,57 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            for a, b, c, r in self.samples:
+                sm.append(a); mx.append(b); pw.append(c); reasons |= r
+            src = "nvml 5 ms"
+        else:
+            if not self.proc:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            self.proc.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            src = "nvidia-smi -lms 20"
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        load = [s_ for s_, p_ in zip(sm, pw) if p_ >= 0.5 * max(pw)] or sm
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": src, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
+def l2_check(rec, u_gpu, n=16):
+    """a QP counts as solved when its status says so AND a sampled subset passes L2 -- forces within
+    1e-3 relative / 1e-2 N of the exact optimum of the reference's QP (oracle/exact.py; the oracle is the checker here,
+    never the thing measured)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import force_error, oracle_solution
+    idx = np.unique(np.linspace(0, rec.B - 1, n).astype(int))
+    worst_abs, worst_rel = 0.0, 0.0
+    for b in idx:
+        o = oracle_solution(rec, int(b))
+        err, rel = force_error(np.asarray(u_gpu[b]).reshape(-1), o["sol"]["U"])
+        worst_abs, worst_rel = max(worst_abs, float(err)), max(worst_rel, float(rel))
+    return {"n": int(len(idx)), "max_abs_err_N": worst_abs, "max_err_over_tolerance": worst_rel, "pass": bool(worst_rel < 1.0),
+            "tolerance": "1e-2 N + 1e-3 |u*| per force component, against the oracle's exact optimum"}
+
+
 def cpu_baseline(rec, budget_s=15.0, eps=1e-5):
     """Oracle C port (OSQP restatement on the reference's sparse QP) on the host cores, bounded sample."""
     from oracle import cpu_port
@@ -267,6 +330,7 @@ def main():
     max_stance = 4 * (int(np.floor(rec.duty * N)) + 1)        # periodic-gait bound on stance foot-steps
     traj = BatchedComTraj.from_records(rec, device=dev)
     mpc = CentroidalMPC(None, traj, verbose=False, mode=args.mode, max_stance=max_stance, device=dev, prepass=args.prepass)
+    _lib.check(lib.cmpc_set_profile(mpc._h, 1))          # per-kernel CUDA events inside cmpc_solve
 
     if args.sweep:
         sweep(args, mpc, records, BatchedComTraj, CentroidalMPC, dev, max_stance)
@@ -284,10 +348,13 @@ def main():
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
-    kern_ms = []
+    kern_ms, k_pre, k_con = [], [], []
+    a_ms, b_ms = ctypes.c_double(), ctypes.c_double()
     for i in range(args.steps):
         step()
         kern_ms.append(mpc.kernel_ms)
+        if lib.cmpc_last_kernel_ms(mpc._h, ctypes.byref(a_ms), ctypes.byref(b_ms)) == 0:
+            k_pre.append(a_ms.value); k_con.append(b_ms.value)
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop()
@@ -297,11 +364,15 @@ def main():
     value = world * B * args.steps / (total_ms * 1e-3)
 
     status = mpc._status.cpu().numpy()
+    u_final = mpc._u.cpu().numpy()
     iters = mpc._iters.cpu().numpy()
     stats = mpc._stats.cpu().numpy()
-    flops = roofline.batch_flops(stats, iters, N)
-    flops_route = roofline.batch_flops(stats, iters, N, route_actual=True)
+    flops = roofline.batch_flops(stats, iters, N, prepass=args.prepass)
+    flops_route = roofline.batch_flops(stats, iters, N, route_actual=True, prepass=args.prepass)
+    f_pre, f_con = roofline.split_flops(stats, iters, N, prepass=args.prepass)
     kms = float(np.mean(kern_ms))
+    pre_ms = float(np.mean(k_pre)) if k_pre else None
+    con_ms = float(np.mean(k_con)) if k_con else None
 
     # ---- end-to-end through the host-buffer C-ABI call ------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -327,6 +398,37 @@ def main():
     d2h = sum(t.numel() * t.element_size() for t in out)
     assert (out[1].numpy() == status).all()
 
+    # ---- second end-to-end figure: the whole cycle from state + command (cmpc_cycle_host), first-step forces out --------
+    e2e_cycle = None
+    try:
+        g = records.random_cycle_inputs(B, seed=4242 + rank)
+        cb = {k: pin(v) for k, v in g.items() if k != "hip"}
+        out_c = (torch.empty(B, 12, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory(),
+                 torch.empty(B, dtype=torch.int32).pin_memory())
+        pos0 = g["pos_des"].copy()
+
+        def step_cycle():
+            mpc_h._warm_host = 0
+            cb["pos_des"].numpy()[:] = pos0
+            return mpc_h.cycle_host(cb["x0"], cb["R_wb"], cb["lever"], cb["cmd"], cb["t0"], cb["pos_des"], cb["I_world"], cb["mass"],
+                                    rec.dt, g["hip"], gait_hz=rec.gait_hz, duty=rec.duty, first_step_only=True, out=out_c)
+
+        for _ in range(max(args.warmup, 3)):
+            step_cycle()
+        barrier()
+        t0c = time.perf_counter()
+        for _ in range(args.steps):
+            step_cycle()
+        barrier()
+        c_ms = max_over_ranks((time.perf_counter() - t0c) * 1e3)
+        e2e_cycle = {"value": world * B * args.steps / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms / args.steps,
+                     "h2d_bytes_per_step": int(sum(cb[k].numel() * 8 for k in cb)), "d2h_bytes_per_step": int(B * (12 * 8 + 3 * 8 + 8)),
+                     "solved_frac": float((out_c[1].numpy() == 1).mean()),
+                     "api": "CentroidalMPC.cycle_host -> cmpc_cycle_host: state + command in (408 B/robot), ComTraj.generate_traj on the "
+                            "device, first-step forces U_opt[:,0] out (96 B/robot); cold start every step"}
+    except Exception as e:
+        e2e_cycle = {"error": repr(e)}
+
     # ---- statistics gathered across ranks (the only collective of the run) ----------------------
     recs = sharding.gather_stats(sharding.local_stats(status, iters, stats, total_ms, flops, flops_route), device=dev)
     summ = sharding.reduce_stats(recs)
@@ -348,7 +450,7 @@ def main():
         traffic, traffic_src = None, None
         try:
             import glob, re
-            caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_v*_dram_traffic.json")),
+            caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_*_dram_traffic.json")),
                           key=lambda f: [int(x) for x in re.findall(r"\d+", os.path.basename(f))])
             tr = json.load(open(caps[-1]))                      # the newest committed capture
             if N == 16 and args.mode == "active_set":
@@ -356,6 +458,37 @@ def main():
                 traffic_src = f"profiles/{os.path.basename(caps[-1])} (ncu dram__bytes_read.sum + dram__bytes_write.sum, scaled per robot)"
         except Exception:
             pass
+        pre_name = {4: "wrench_pdas_kernel", 3: "riccati2_lockstep_kernel", 2: "riccati2_kernel", 1: "riccati_kernel"}.get(args.prepass)
+        kernels = []
+        if pre_name and pre_ms:
+            kernels.append({"name": pre_name, "ms": pre_ms, "algorithmic_flops": f_pre,
+                            "achieved": f_pre / (pre_ms * 1e-3) / 1e12, "frac": f_pre / (pre_ms * 1e-3) / 1e12 / f64.value,
+                            "robots_finished": int(np.isin(stats[:, 7].astype(int), (4, 5)).sum())})
+        if con_ms is not None:
+            kernels.append({"name": "solve_fast_kernel", "ms": con_ms, "algorithmic_flops": f_con,
+                            "achieved": f_con / (max(con_ms, 1e-6) * 1e-3) / 1e12,
+                            "frac": f_con / (max(con_ms, 1e-6) * 1e-3) / 1e12 / f64.value,
+                            "robots_finished": int((~np.isin(stats[:, 7].astype(int), (4, 5))).sum())})
+        dom = max(kernels, key=lambda k_: k_["ms"]) if kernels else None
+        ach_route = flops_route / (kms * 1e-3) / 1e12
+        roof = {"bound": "fp64_fma",
+                "kernel": (dom["name"] if dom else "solve_fast_kernel") + " (dominant kernel of one cmpc_solve call)",
+                "achieved": dom["achieved"] if dom else ach_route, "peak": f64.value, "unit": "TFLOP/s",
+                "frac": dom["frac"] if dom else ach_route / f64.value,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel_ms": dom["ms"] if dom else kms, "algorithmic_flops_per_launch": dom["algorithmic_flops"] if dom else flops_route,
+                "kernels": kernels,
+                "whole_solve": {"ms": kms, "algorithmic_flops": flops_route, "achieved": ach_route, "frac": ach_route / f64.value},
+                "frac_condensed_route_figure": ach_tf / f64.value,
+                "note": "frac = algorithmic flops of the route every robot really took (convex_mpc_b200/roofline.py: 6.8 kFLOP per stage and "
+                        "sweep + 0.7 kFLOP per stage for the certificate on the Riccati route; Cholesky / active-set / ADMM counts on the "
+                        "condensed route) / live CUDA-event duration of that kernel / measured DFMA peak; "
+                        "frac_condensed_route_figure charges every robot the condensed route's flops (SURVEY 8d per-unit figure, round-1 comparable)",
+                "peak_source": "cmpc_microbench DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "smem_gbs_measured": smem.value,
+                "hbm": {"achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "algorithmic_bytes_per_launch": alg_bytes}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "p50_batch_ms": float(np.median(per_step)),
@@ -367,21 +500,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "CentroidalMPC.solve_host -> cmpc_solve_host (pinned host buffers)"},
+            "e2e_cycle": e2e_cycle,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64_fma", "kernel": "riccati2_lockstep_kernel + solve_fast_kernel (one cmpc_solve call)" if args.prepass else "solve_fast_kernel", "achieved": ach_tf, "peak": f64.value,
-                         "unit": "TFLOP/s", "frac": ach_tf / f64.value, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel_ms": kms, "algorithmic_flops_per_launch": flops,
-                         "frac_route_actual": flops_route / (kms * 1e-3) / 1e12 / f64.value,
-                         "note": "frac counts every robot at the condensed route's flops (SURVEY 8d per-unit figure); "
-                                 "frac_route_actual counts robots finished by the Riccati pre-pass at that sweep's (4.5x smaller) flops; "
-                                 "kernel_ms = pre-pass + condensed kernel of one cmpc_solve call",
-                         "peak_source": "cmpc_microbench DFMA stream measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                         "smem_gbs_measured": smem.value,
-                         "hbm": {"achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                                 "algorithmic_bytes_per_launch": alg_bytes}},
+            "roofline": roof,
             "solver": {k: summ[k] for k in ("solved", "max_iter", "inaccurate", "failed", "path_unconstrained",
-                                            "path_active_set", "path_admm", "path_admm_polish", "path_riccati", "r_prim_max", "r_dual_max")},
+                                            "path_active_set", "path_admm", "path_admm_polish", "path_riccati", "path_wrench_as", "r_prim_max", "r_dual_max")},
         }
         line["solver"]["as_iters_mean"] = summ["as_iters_sum"] / max(summ["qps_count"], 1)
         line["solver"]["n_free_mean"] = summ["n_free_sum"] / max(summ["qps_count"], 1)
@@ -423,6 +546,10 @@ def main():
         line["extra"] = extra
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(rec)
+        try:
+            line["solver"]["l2_check"] = l2_check(rec, u_final, 16)
+        except Exception as e:
+            line["solver"]["l2_check"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

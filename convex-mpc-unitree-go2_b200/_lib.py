@@ -24,6 +24,8 @@ PROTOTYPES = {
                                 c_double, c_double, c_double, c_int, c_int, c_int, c_int]),
     "cmpc_set_max_stance": (c_int, [c_void_p, c_int]),
     "cmpc_set_generic": (c_int, [c_void_p, c_int]),
+    "cmpc_set_profile": (c_int, [c_void_p, c_int]),
+    "cmpc_last_kernel_ms": (c_int, [c_void_p, c_dp, c_dp]),
     "cmpc_set_prepass": (c_int, [c_void_p, c_int]),
     "cmpc_workspace_bytes": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "cmpc_reserve": (c_int, [c_void_p, c_int]),
@@ -42,6 +44,8 @@ PROTOTYPES = {
                    [c_void_p] * 8 + [c_void_p]),
     "cmpc_solve_host": (c_int, [c_void_p, c_int] + [c_void_p] * 6 + [c_double, c_double, c_double, c_dp,
                                                                     c_int, c_void_p, c_void_p, c_void_p]),
+    "cmpc_cycle_host": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_double, c_double, c_double, c_dp, c_dp,
+                                                                    c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cmpc_host_stats": (c_int, [c_void_p, c_int, c_void_p]),
     "cmpc_launch_count": (ctypes.c_longlong, []),
     "cmpc_microbench": (c_int, [c_int, c_dp, c_dp]),

@@ -10,6 +10,7 @@ There is no CPU fallback: importing this module without ``libcmpc.so`` raises.
 """
 import ctypes
 import time
+import weakref
 
 import numpy as np
 import torch
@@ -58,8 +59,18 @@ class _DM:
     """Tiny stand-in for ``casadi.DM`` so that ``sol["x"].full().flatten()`` (test_MPC.py:190) works."""
 
     def __init__(self, tensor, batched):
-        self.tensor = tensor
+        # a callable is evaluated on first use: assembling the reference's stacked vectors for 65 536 robots moves ~1 GB
+        # through HBM per cycle, which a caller that only reads ``sol["u"]`` should not pay for
+        self._make = tensor if callable(tensor) else None
+        self._tensor = None if callable(tensor) else tensor
         self._batched = batched
+
+    @property
+    def tensor(self):
+        if self._tensor is None:
+            self._tensor = self._make()
+            self._make = None
+        return self._tensor
 
     def full(self):
         a = self.tensor.detach().cpu().numpy()
@@ -192,7 +203,8 @@ class CentroidalMPC:
         self.kernel_ms = 0.0
         with torch.cuda.device(self.device):
             self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        self.x_prev = self.lam_x_prev = self.lam_a_prev = None
+        self._prev_shape = None          # x_prev / lam_x_prev / lam_a_prev are None until the first solve (centroidal_mpc.py:62-64)
+        self._pending = []
         self.last_stats = None
         if verbose:
             n, N = self.nvars, self.N
@@ -245,7 +257,8 @@ class CentroidalMPC:
         """Forget the warm-start state (the reference has no such call: it warm-starts forever)."""
         self._warm = False
         self._warm_host = 0
-        self.x_prev = self.lam_x_prev = self.lam_a_prev = None
+        self._settle_pending()
+        self._prev_shape = None
 
     # ------------------------------------------------------------------------------------------
     def _batch_of(self, traj):
@@ -358,6 +371,37 @@ class CentroidalMPC:
         return t, use_ab
 
     # ------------------------------------------------------------------------------------------
+    def _stacked(self, B, N, sq):
+        """Makers of the reference's stacked vectors (centroidal_mpc.py:108-110: x (24N), lam_x (24N), lam_a (28N)) from
+        the device buffers; evaluated on first use."""
+        X, u, y, nu, dev = self._X, self._u, self._y, self._nu, self.device
+        return {"x": lambda: sq(torch.cat([X[:B], u[:B]], dim=1)),
+                "lam_x": lambda: sq(torch.cat([torch.zeros(B, 12 * N, dtype=torch.float64, device=dev), y[:B, :12 * N]], dim=1)),
+                "lam_a": lambda: sq(torch.cat([nu[:B], y[:B, 12 * N:]], dim=1))}
+
+    def _settle_pending(self):
+        for ref in getattr(self, "_pending", ()):
+            d = ref()
+            if d is not None:
+                d.tensor
+        self._pending = []
+
+    def _prev(self, key):
+        shp = getattr(self, "_prev_shape", None)
+        if shp is None:
+            return None
+        B, N, batched = shp
+        d = _DM(self._stacked(B, N, (lambda a: a) if batched else (lambda a: a[0]))[key], batched)
+        self._pending.append(weakref.ref(d))
+        return d
+
+    # the reference keeps the raw previous solution for the warm start (centroidal_mpc.py:108-110); here the device
+    # buffers themselves are the warm start, the stacked views are built when somebody asks
+    x_prev = property(lambda self: self._prev("x"))
+    lam_x_prev = property(lambda self: self._prev("lam_x"))
+    lam_a_prev = property(lambda self: self._prev("lam_a"))
+
+    # ------------------------------------------------------------------------------------------
     def solve_QP(self, go2, traj, verbose: bool = False):
         """One MPC cycle for every robot in ``traj`` (centroidal_mpc.py:69-120)."""
         t0 = time.perf_counter()
@@ -368,6 +412,7 @@ class CentroidalMPC:
             raise _lib.CmpcError(f"traj.N = {traj.N} but the solver was built for N = {N}")
         self._alloc_state(B)
         with torch.cuda.device(self.device):
+            self._settle_pending()          # stacked vectors of the previous solution somebody still holds are built now
             stream = torch.cuda.current_stream().cuda_stream
             t, use_ab = self._gather(traj, B, stream)
             torch.cuda.current_stream().synchronize()
@@ -391,11 +436,10 @@ class CentroidalMPC:
 
         batched = B0 > 0
         sq = (lambda a: a) if batched else (lambda a: a[0])
-        zeros = torch.zeros(B, 12 * N, dtype=torch.float64, device=self.device)
         sol = MPCSolution()
-        sol["x"] = _DM(sq(torch.cat([self._X, self._u], dim=1)), batched)
-        sol["lam_x"] = _DM(sq(torch.cat([zeros, self._y[:, :12 * N]], dim=1)), batched)
-        sol["lam_a"] = _DM(sq(torch.cat([self._nu, self._y[:, 12 * N:]], dim=1)), batched)
+        mk = self._stacked(B, N, sq)
+        sol["x"], sol["lam_x"], sol["lam_a"] = (_DM(mk[k], batched) for k in ("x", "lam_x", "lam_a"))
+        self._pending = [weakref.ref(sol[k]) for k in ("x", "lam_x", "lam_a")]
         sol["cost"] = _DM(sq(self._stats[:, 2:3].clone()), batched)
         sol["u"] = sq(self._u.view(B, N, 12).transpose(1, 2))       # (B,12,N): U_opt of test_MPC.py:192
         sol["X"] = sq(self._X.view(B, N, 12).transpose(1, 2))
@@ -404,7 +448,7 @@ class CentroidalMPC:
         sol["stats"] = sq(self._stats)
         sol["r_prim"] = sq(self._stats[:, 0])
         sol["r_dual"] = sq(self._stats[:, 1])
-        self.x_prev, self.lam_x_prev, self.lam_a_prev = sol["x"], sol["lam_x"], sol["lam_a"]
+        self._prev_shape = (B, N, batched)
         self.last_stats = self._stats
         if verbose:
             st = self._status.cpu().numpy()
@@ -468,6 +512,37 @@ class CentroidalMPC:
             host_ptr(I_world, B * 9), host_ptr(mass, B), host_ptr(t0, B), float(dt), float(gait_hz), float(duty),
             _lib.darr(phase_offset), int(self._warm_host),
             u.data_ptr(), st.data_ptr(), it.data_ptr()))
+        self._warm_host = 1 if OPTS.get("warm_start_primal", True) else 0
+        return u, st, it
+
+    def cycle_host(self, x0, R_world_to_body, foot_lever, cmd, t0, pos_des, I_world, mass, dt, hip_offset,
+                   gait_hz=3.0, duty=0.6, phase_offset=PHASE_OFFSET, first_step_only=False, out=None):
+        """One whole MPC cycle from HOST state + command through ``cmpc_cycle_host``: reference trajectory and lever arms
+        (``ComTraj.generate_traj``, com_trajectory.py:27-211), contact table, QP solve, and the slice
+        ``U_opt = w[12N:]`` of test_MPC.py:189-196 -- 408 bytes in per robot, 96 bytes out with ``first_step_only``.
+
+        Inputs: C-contiguous float64 numpy arrays or CPU torch tensors (pinned memory gives true overlap);
+        ``pos_des`` (B,3) is updated in place.  Returns ``(u, status, iters)`` (``u`` (B,12) or (B,12N))."""
+        def host_ptr(a, n):
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == n
+                return a.data_ptr()
+            a = np.asarray(a)
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == n
+            return a.ctypes.data
+        N = self.N
+        B = int(np.prod(tuple(mass.shape)))
+        w = 12 if first_step_only else 12 * N
+        if out is None:
+            out = (torch.empty(B, w, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory(),
+                   torch.empty(B, dtype=torch.int32).pin_memory())
+        u, st, it = out
+        assert u.numel() == B * w
+        check(self._lib.cmpc_cycle_host(
+            self._h, B, host_ptr(x0, B * 12), host_ptr(R_world_to_body, B * 9), host_ptr(foot_lever, B * 12),
+            host_ptr(cmd, B * 4), host_ptr(t0, B), host_ptr(pos_des, B * 3), host_ptr(I_world, B * 9), host_ptr(mass, B),
+            float(dt), float(gait_hz), float(duty), _lib.darr(phase_offset), _lib.darr(np.asarray(hip_offset, dtype=np.float64).reshape(-1)),
+            int(self._warm_host), int(bool(first_step_only)), u.data_ptr(), st.data_ptr(), it.data_ptr()))
         self._warm_host = 1 if OPTS.get("warm_start_primal", True) else 0
         return u, st, it
 

@@ -534,6 +534,10 @@ struct cmpc_handle {
     };
     Slot slot[4];
     std::atomic<unsigned> slot_next{0};
+    // per-kernel timing of cmpc_solve (cmpc_set_profile): events before the pre-pass, between the two kernels and after
+    int profile = 0;
+    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
+    int pev_valid = 0;
     int reserved_batch = 0;         // robots the slots are sized for (0 = not reserved yet)
     int reserved_nfmax = 0;
     size_t yg_stride = 0, hp_stride = 0, hp_stride_generic = 0;
@@ -547,6 +551,7 @@ struct cmpc_handle {
         uint64_t* mask = nullptr;
         double *u = nullptr, *y = nullptr, *rho = nullptr, *stats = nullptr;
         int32_t *status = nullptr, *iters = nullptr;
+        double *R_wb = nullptr, *lever = nullptr, *cmd = nullptr, *pos_des = nullptr;      // cmpc_cycle_host only
         cudaStream_t s[2] = {nullptr, nullptr};
     } hp;
 };
@@ -716,9 +721,11 @@ int cmpc_destroy(cmpc_handle* h) {
     cudaSetDevice(h->device);
     free_slots(h);
     auto& q = h->hp;
-    void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters};
+    void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters,
+                    q.R_wb, q.lever, q.cmd, q.pos_des};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto s : q.s) if (s) cudaStreamDestroy(s);
+    for (auto e : h->pev) if (e) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -745,6 +752,27 @@ int cmpc_set_max_stance(cmpc_handle* h, int nfmax) {
     if (nfmax < 4) nfmax = 4;
     if (nfmax > 4 * h->N) nfmax = 4 * h->N;
     h->nfmax = nfmax;
+    return 0;
+}
+
+int cmpc_set_profile(cmpc_handle* h, int on) {
+    if (!h) return fail("null handle");
+    CU_TRY(cudaSetDevice(h->device));
+    if (on && !h->pev[0]) for (auto& e : h->pev) CU_TRY(cudaEventCreate(&e));
+    h->profile = on ? 1 : 0;
+    h->pev_valid = 0;
+    return 0;
+}
+
+int cmpc_last_kernel_ms(cmpc_handle* h, double* prepass_ms, double* condensed_ms) {
+    if (!h || !prepass_ms || !condensed_ms) return fail("null argument");
+    if (!h->profile || !h->pev_valid) return fail("no profiled solve on this handle (cmpc_set_profile, then cmpc_solve with raw inputs)");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaEventSynchronize(h->pev[2]));
+    float a = 0.f, b = 0.f;
+    CU_TRY(cudaEventElapsedTime(&a, h->pev[0], h->pev[1]));
+    CU_TRY(cudaEventElapsedTime(&b, h->pev[1], h->pev[2]));
+    *prepass_ms = a; *condensed_ms = b;
     return 0;
 }
 
@@ -944,6 +972,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         const int* wlc = nullptr;
         // small batches are latency-bound (fewer robots than CTA slots x a few rounds): the extra kernel in front only
         // adds to the latency there (batch 1: 45 -> 99 us), so the pre-pass starts at prepass_min_batch robots
+        if (h->profile) { CU_TRY(cudaEventRecord(h->pev[0], st)); CU_TRY(cudaEventRecord(h->pev[1], st)); h->pev_valid = 0; }
         if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET && B >= h->prepass_min_batch) {
             CU_TRY(cudaMemsetAsync(sl.ctl, 0, 4 * sizeof(int), st));
             bool launched = false;
@@ -1006,12 +1035,14 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 wl = sl.worklist; wlc = sl.ctl;
                 const int cap_f = h->sm_count * 2;
                 grid_f = B < cap_f ? B : cap_f;
+                if (h->profile) CU_TRY(cudaEventRecord(h->pev[1], st));
             }
         }
         if (hstride) solve_fast_kernel<true><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, sl.hp, hstride, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
         else solve_fast_kernel<false><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, nullptr, 0, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
         ++g_launches;
         CU_TRY(cudaGetLastError());
+        if (h->profile) { CU_TRY(cudaEventRecord(h->pev[2], st)); h->pev_valid = 1; }
         return 0;
     }
     const size_t stride = hp_stride_generic(h, h->nfmax);
@@ -1026,14 +1057,8 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
     return 0;
 }
 
-int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref, const double* r_foot,
-                    const double* I_world, const double* mass, const double* t0, double dt, double gait_hz,
-                    double duty, const double phase_offset[4], int warm, double* u, int32_t* status, int32_t* iters) {
-    if (!h || !x0 || !x_ref || !r_foot || !I_world || !mass || !t0 || !phase_offset || !u || !status || !iters)
-        return fail("null argument");
-    if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");
-    if (B == 0) return 0;
-    CU_TRY(cudaSetDevice(h->device));
+// device-resident buffers of the *_host entries, sized for max_batch robots on first use
+static int host_path_ready(cmpc_handle* h) {
     const int N = h->N;
     auto& q = h->hp;
     if (!q.ready) {
@@ -1055,16 +1080,36 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
         CU_TRY(cudaMemset(q.u, 0, mb * 12 * N * sizeof(double)));
         CU_TRY(cudaMemset(q.y, 0, mb * 28 * N * sizeof(double)));
         for (auto& s : q.s) CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CU_TRY(cudaMalloc(&q.R_wb, mb * 9 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.lever, mb * 12 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.cmd, mb * 4 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.pos_des, mb * 3 * sizeof(double)));
         q.ready = true;
     }
+    return 0;
+}
+
+int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref, const double* r_foot,
+                    const double* I_world, const double* mass, const double* t0, double dt, double gait_hz,
+                    double duty, const double phase_offset[4], int warm, double* u, int32_t* status, int32_t* iters) {
+    if (!h || !x0 || !x_ref || !r_foot || !I_world || !mass || !t0 || !phase_offset || !u || !status || !iters)
+        return fail("null argument");
+    if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    const int N = h->N;
+    auto& q = h->hp;
+    if (host_path_ready(h)) return -1;
     // chunks sized so that copies of one chunk hide behind the solve of the other
-    int chunk = B <= 4096 ? B : (B < 32768 ? 8192 : 16384);   // measured at 65 536 robots: 4096 -> 12.3 ms, 8192 -> 11.6, 16384 -> 11.3, 32768 -> 11.9
+    // measured at 65 536 robots with the round-2 kernels (tools/host_path_probe.py): one chunk 9.3 ms, 32768 -> 7.4, 16384 -> 7.7,
+    // 8192 -> 9.5, 4096 -> 13.5 (a chunk's kernel cannot end before its slowest robot has, so small chunks cost tails)
+    int chunk = B <= 8192 ? B : (B < 65536 ? (B + 1) / 2 : 32768);
     if (const char* e = getenv("CMPC_HOST_CHUNK")) { const int v = atoi(e); if (v >= 256) chunk = v < B ? v : B; }   // tuning
     // the first copy in and the last copy out cannot hide behind anything: ramp the chunk size up from 4 096
     // (4096, 8192, then `chunk`) and finish with a 4 096-robot chunk, so that only small transfers are exposed
-    const bool ramp = (B >= 4 * chunk) && !getenv("CMPC_HOST_CHUNK");
-    int ci = 0, nb = 0;
-    for (int lo = 0; lo < B; lo += nb, ++ci) {
+    const bool ramp = (B >= 8 * chunk) && !getenv("CMPC_HOST_CHUNK");
+    int ci = 0, nb = 0, rc = 0;
+    for (int lo = 0; lo < B && !rc; lo += nb, ++ci) {
         int want = chunk;
         if (ramp) {
             if (ci == 0) want = 4096;
@@ -1075,27 +1120,81 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
         nb = (B - lo) < want ? (B - lo) : want;
         cudaStream_t s = q.s[ci & 1];
         const size_t o = (size_t)lo;
-        CU_TRY(cudaMemcpyAsync(q.x0 + o * 12, x0 + o * 12, (size_t)nb * 12 * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(q.x_ref + o * 12 * N, x_ref + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(q.r_foot + o * 12 * N, r_foot + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(q.I_world + o * 9, I_world + o * 9, (size_t)nb * 9 * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(q.mass + o, mass + o, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(q.t0 + o, t0 + o, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, s));
-        if (cmpc_contact_table(h, nb, q.t0 + o, dt, gait_hz, duty, phase_offset, q.mask + o * h->W, s)) return -1;
-        if (cmpc_solve(h, nb, nullptr, nullptr, nullptr, q.x0 + o * 12, q.x_ref + o * 12 * N, q.r_foot + o * 12 * N,
+        auto up = [&](double* d, const double* src, size_t w) {
+            return cudaMemcpyAsync(d + o * w, src + o * w, (size_t)nb * w * sizeof(double), cudaMemcpyHostToDevice, s);
+        };
+        if (up(q.x0, x0, 12) || up(q.x_ref, x_ref, (size_t)12 * N) || up(q.r_foot, r_foot, (size_t)12 * N) || up(q.I_world, I_world, 9) ||
+            up(q.mass, mass, 1) || up(q.t0, t0, 1)) { rc = fail("host-to-device copy failed"); break; }
+        if (cmpc_contact_table(h, nb, q.t0 + o, dt, gait_hz, duty, phase_offset, q.mask + o * h->W, s) ||
+            cmpc_solve(h, nb, nullptr, nullptr, nullptr, q.x0 + o * 12, q.x_ref + o * 12 * N, q.r_foot + o * 12 * N,
                        q.I_world + o * 9, q.mass + o, dt, q.mask + o * h->W, warm, q.u + o * 12 * N, q.y + o * 28 * N,
-                       q.rho + o, nullptr, nullptr, q.status + o, q.iters + o, q.stats + o * CMPC_NSTAT, s))
-            return -1;
-        CU_TRY(cudaMemcpyAsync(u + o * 12 * N, q.u + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(status + o, q.status + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(iters + o, q.iters + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                       q.rho + o, nullptr, nullptr, q.status + o, q.iters + o, q.stats + o * CMPC_NSTAT, s)) { rc = -1; break; }
+        cudaError_t e = cudaMemcpyAsync(u + o * 12 * N, q.u + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status + o, q.status + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(iters + o, q.iters + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e)); break; }
     }
-    CU_TRY(cudaStreamSynchronize(q.s[0]));
-    CU_TRY(cudaStreamSynchronize(q.s[1]));
+    // copies from / to the caller's buffers may still be in flight: never return before both streams have drained
+    const cudaError_t e0 = cudaStreamSynchronize(q.s[0]), e1 = cudaStreamSynchronize(q.s[1]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess) return fail(cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
     return 0;
 }
 
-/* stats of the last cmpc_solve_host call stay on the device; copy them out on request */
+int cmpc_cycle_host(cmpc_handle* h, int B, const double* x0, const double* R_world_to_body, const double* foot_lever,
+                    const double* cmd, const double* t0, double* pos_des, const double* I_world, const double* mass,
+                    double dt, double gait_hz, double duty, const double phase_offset[4], const double hip_offset[12],
+                    int warm, int first_step_only, double* u, int32_t* status, int32_t* iters) {
+    if (!h || !x0 || !R_world_to_body || !foot_lever || !cmd || !t0 || !pos_des || !I_world || !mass || !phase_offset ||
+        !hip_offset || !u || !status || !iters)
+        return fail("null argument");
+    if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(h->device));
+    if (host_path_ready(h)) return -1;
+    const int N = h->N;
+    auto& q = h->hp;
+    // 408 bytes in and 96 (first step) or 96 N bytes out per robot: two halves on two streams are enough to overlap
+    // what little is copied with the kernels
+    // (full-horizon forces out: 1.5 KB per robot, worth overlapping; first step only: one chunk, one kernel tail)
+    const int nchunk = (B >= 8192 && !first_step_only) ? 2 : 1;
+    const int per = (B + nchunk - 1) / nchunk;
+    int rc = 0;
+    for (int ci = 0; ci < nchunk && !rc; ++ci) {
+        const int lo = ci * per, nb = (B - lo) < per ? (B - lo) : per;
+        if (nb <= 0) break;
+        cudaStream_t s = q.s[ci & 1];
+        const size_t o = (size_t)lo;
+        auto up = [&](double* d, const double* src, size_t w) {
+            return cudaMemcpyAsync(d + o * w, src + o * w, (size_t)nb * w * sizeof(double), cudaMemcpyHostToDevice, s);
+        };
+        if (up(q.x0, x0, 12) || up(q.R_wb, R_world_to_body, 9) || up(q.lever, foot_lever, 12) || up(q.cmd, cmd, 4) ||
+            up(q.t0, t0, 1) || up(q.pos_des, pos_des, 3) || up(q.I_world, I_world, 9) || up(q.mass, mass, 1)) { rc = fail("host-to-device copy failed"); break; }
+        if (cmpc_generate_traj(h->device, N, nb, q.x0 + o * 12, q.R_wb + o * 9, q.lever + o * 12, q.cmd + o * 4, q.t0 + o, dt,
+                               gait_hz, duty, phase_offset, hip_offset, q.pos_des + o * 3, q.pos_des + o * 3,
+                               q.x_ref + o * 12 * N, q.r_foot + o * 12 * N, s) ||
+            cmpc_contact_table(h, nb, q.t0 + o, dt, gait_hz, duty, phase_offset, q.mask + o * h->W, s) ||
+            cmpc_solve(h, nb, nullptr, nullptr, nullptr, q.x0 + o * 12, q.x_ref + o * 12 * N, q.r_foot + o * 12 * N,
+                       q.I_world + o * 9, q.mass + o, dt, q.mask + o * h->W, warm, q.u + o * 12 * N, q.y + o * 28 * N,
+                       q.rho + o, nullptr, nullptr, q.status + o, q.iters + o, q.stats + o * CMPC_NSTAT, s)) { rc = -1; break; }
+        cudaError_t e;
+        if (first_step_only)       // U_opt[:, 0], the only column the consumer applies (test_MPC.py:196)
+            e = cudaMemcpy2DAsync(u + o * 12, 12 * sizeof(double), q.u + o * 12 * N, (size_t)12 * N * sizeof(double),
+                                  12 * sizeof(double), (size_t)nb, cudaMemcpyDeviceToHost, s);
+        else
+            e = cudaMemcpyAsync(u + o * 12 * N, q.u + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pos_des + o * 3, q.pos_des + o * 3, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status + o, q.status + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(iters + o, q.iters + o, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { rc = fail(cudaGetErrorString(e)); break; }
+    }
+    // copies from / to the caller's buffers may still be in flight: never return before both streams have drained
+    const cudaError_t e0 = cudaStreamSynchronize(q.s[0]), e1 = cudaStreamSynchronize(q.s[1]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess) return fail(cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return 0;
+}
+
 int cmpc_host_stats(cmpc_handle* h, int B, double* stats_host) {
     if (!h || !stats_host || !h->hp.ready) return fail("no host-path state");
     if (B < 0 || B > h->max_batch) return fail("batch exceeds max_batch of the handle");

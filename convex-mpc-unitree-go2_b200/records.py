@@ -141,6 +141,37 @@ def random_records(B, N=16, seed=None, gait_hz=3.0, duty=0.6, stress=0.0):
     return Records(x0, x_ref, r_foot, I_world, mass, t0, dt, gait_hz, duty, N)
 
 
+GO2_HIP_OFFSET = np.array([[0.1934, 0.0465, 0.0], [0.1934, -0.0465, 0.0], [-0.1934, 0.0465, 0.0], [-0.1934, -0.0465, 0.0]])
+GO2_STANCE_OFFSET = np.array([[0.1934, 0.142, 0.0], [0.1934, -0.142, 0.0], [-0.1934, 0.142, 0.0], [-0.1934, -0.142, 0.0]])
+
+
+def random_cycle_inputs(B, seed=None):
+    """Robot states + commands of one MPC cycle as test_MPC.py:173-196 feeds them (host arrays for
+    ``CentroidalMPC.cycle_host`` / ``cmpc_cycle_host``): the same distributions as ``random_records`` (SURVEY.md 8d
+    config #3), but BEFORE ``ComTraj.generate_traj`` -- 408 bytes per robot instead of the 3.3 KB record."""
+    rng = np.random.default_rng(seed)
+    so, hip = GO2_STANCE_OFFSET, GO2_HIP_OFFSET
+    yaw = rng.uniform(-np.pi, np.pi, B)
+    x = np.zeros((B, 12))
+    x[:, 0:2] = rng.uniform(-5, 5, (B, 2)); x[:, 2] = 0.27 + rng.normal(0, 0.01, B); x[:, 5] = yaw
+    x[:, 3:5] = np.clip(rng.normal(0, 0.05, (B, 2)), -0.15, 0.15)
+    cmd = np.stack([rng.uniform(-0.8, 0.8, B), rng.uniform(-0.4, 0.4, B), np.full(B, 0.27), rng.uniform(-4, 4, B)], axis=1)
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    x[:, 6] = c * cmd[:, 0] - s_ * cmd[:, 1]; x[:, 7] = s_ * cmd[:, 0] + c * cmd[:, 1]
+    x[:, 6:9] += rng.normal(0, 0.1, (B, 3))
+    x[:, 9:12] = rng.normal(0, 0.2, (B, 3)); x[:, 11] += cmd[:, 3]
+    R = _rot_zyx(x[:, 3], x[:, 4], x[:, 5])
+    lever = np.zeros((B, 4, 3))
+    for leg in range(4):
+        lever[:, leg, 0] = c * so[leg, 0] - s_ * so[leg, 1]
+        lever[:, leg, 1] = s_ * so[leg, 0] + c * so[leg, 1]
+        lever[:, leg, 2] = -x[:, 2]
+    lever[:, :, 0:2] += rng.normal(0, 0.03, (B, 4, 2))
+    t0 = 1e-3 * rng.integers(0, 10000, B).astype(np.float64)
+    return dict(x0=x, R_wb=np.ascontiguousarray(np.swapaxes(R, 1, 2)), lever=lever, cmd=cmd, t0=t0, pos_des=x[:, 0:3].copy(),
+                I_world=np.ascontiguousarray(np.einsum("bij,j,bkj->bik", R, GO2_I_BODY, R)), mass=np.full(B, GO2_MASS), hip=hip)
+
+
 def srb_closed_loop_step(rec, Ad, Bd, gd, u0, mpc_period=0.02, rng=None, noise=0.0):
     """Advance every robot by one MPC period with the first-step forces (stand-in for MuJoCo,
     SURVEY.md section 8f-2): x+ = x + (mpc_period/dt) * (Ad x + Bd[0] u0 + gd - x), then rebuild the

@@ -44,20 +44,47 @@ def riccati_flops_per_qp(n, N=16):
     return N * stage + 48 * n + 24 * N + 2 * (2 * 144 * N + 24 * n) + 4 * n
 
 
-def batch_flops(stats, iters, N=16, route_actual=False):
+def wrench_flops_per_qp(sweeps, N=16):
+    """Work of the wrench-space projected-Riccati active-set route (csrc/cmpc_wrench.cuh) for a robot that needed
+    ``sweeps`` backward + forward sweeps, counted once per robot (the kernel's four threads repeat the 6 x 6
+    factorizations; the repeats are not algorithmic work).  Per backward stage, in fused multiply-adds:
+    S = P Bbar 180, Gbar = Bbar'S 52, Lam_k / what_k from the four feet 264, ghat and Bbar'q 96, two 6 x 6 Cholesky
+    factorizations 112, Nn = I + L'Lam L 217, the five triangular solves of the twelve rows of S and of Bbar'q
+    13 * 105 = 1365, the symmetric update P - S Phi S' 468, D A and A'(D A) 150, the vector recursion 96: 3 000 FMA
+    = 6.0 kFLOP.  Per forward stage (wrench co-state, four foot projections, multipliers, roll-out) 400 FMA = 0.8 kFLOP.
+    The certificate pass (co-states, stationarity, feasibility from first principles) 350 FMA = 0.7 kFLOP per stage."""
+    sweeps = np.asarray(sweeps, dtype=np.float64)
+    return sweeps * N * (6.0e3 + 0.8e3) + N * 0.7e3 + 1.0e3
+
+
+def batch_flops(stats, iters, N=16, route_actual=False, prepass=3):
     """Total algorithmic flops of a batch from the (B, NSTAT) stats array and the ADMM iteration counts.
     Robots finished by the Riccati pre-pass (path 4) count at the condensed route's figure for an unconstrained
     robot -- the per-unit figure of SURVEY.md section 8(d), comparable across kernel versions -- unless
     ``route_actual`` asks for the flops of the route they really took."""
     stats = np.asarray(stats)
     path = stats[:, 7].astype(np.int64)
-    ric = path == 4
+    ric = (path == 4) | (path == 5)
     path = np.where(ric, 0, path)
     admm = (path >= 2)
     f = flops_per_qp(stats[:, 3], path, stats[:, 6], stats[:, 4], np.asarray(iters) * admm, admm.astype(np.float64), N)
     if route_actual:
         f = np.where(ric, riccati_flops_per_qp(stats[:, 3], N), f)
+        if prepass == 4:
+            p0 = stats[:, 7].astype(np.int64)
+            wr = (p0 == 4) | (p0 == 5)
+            f = np.where(wr, wrench_flops_per_qp(stats[:, 6] + 1.0, N), f)
     return float(f.sum())
+
+
+def split_flops(stats, iters, N=16, prepass=4):
+    """(flops finished by the pre-pass kernel, flops of the condensed kernel) at the route each robot took."""
+    stats = np.asarray(stats)
+    p0 = stats[:, 7].astype(np.int64)
+    pre = (p0 == 4) | (p0 == 5)
+    a = batch_flops(stats[pre], np.asarray(iters)[pre], N, route_actual=True, prepass=prepass) if pre.any() else 0.0
+    b = batch_flops(stats[~pre], np.asarray(iters)[~pre], N, route_actual=True, prepass=prepass) if (~pre).any() else 0.0
+    return a, b
 
 
 def bytes_per_qp(N=16):

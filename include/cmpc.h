@@ -87,6 +87,13 @@ int cmpc_set_generic(cmpc_handle* h, int on);
  * Batches below 2 048 robots skip the pre-pass (they are latency-bound; the extra launch only adds latency).  */
 int cmpc_set_prepass(cmpc_handle* h, int on);
 
+/* Measurement aid (bench.py, SURVEY.md section 8d: per-kernel roofline fractions measured live): with profiling on,
+ * cmpc_solve (raw inputs) records CUDA events on its stream before the pre-pass kernel, between the two kernels and
+ * after the condensed kernel; cmpc_last_kernel_ms waits for the last such solve and returns the two durations.
+ * The reference's counterpart are the wall-clock timers of centroidal_mpc.py:102-105. */
+int cmpc_set_profile(cmpc_handle* h, int on);
+int cmpc_last_kernel_ms(cmpc_handle* h, double* prepass_ms, double* condensed_ms);
+
 /* Workspace (section 8b "no allocation inside solve").  A handle keeps four SLOTS of device workspace (work-list,
  * counters, gain scratch, L2-resident scratch of the condensed kernel); consecutive cmpc_solve / cmpc_build calls
  * rotate over them, so AT MOST FOUR calls of one handle may be in flight at a time (on any streams), and calls on
@@ -181,7 +188,20 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
                     const double phase_offset[4], int warm,
                     double* u, int32_t* status, int32_t* iters);
 
-/* Per-QP statistics (B, CMPC_NSTAT) of the last cmpc_solve_host call, copied to the host. */
+/* One whole MPC cycle from the robot's state and command on the HOST: what test_MPC.py:173-196 does per cycle --
+ * ComTraj.generate_traj (com_trajectory.py:27-211), the contact table (gait.py:26-37), solve_QP
+ * (centroidal_mpc.py:69-120) and the slice U_opt = w[12N:] (test_MPC.py:189-192) -- with the reference trajectory and
+ * lever arms generated on the device: 408 bytes in per robot (x0 12, R_world_to_body 9, foot_lever 12, cmd 4, t0 1,
+ * pos_des 3, I_world 9, mass 1 doubles) instead of the 3.3 KB record of cmpc_solve_host.  pos_des (B,3) is read and
+ * written back (the clamped world position target ComTraj carries from cycle to cycle, com_trajectory.py:47-61).
+ * first_step_only != 0: u is (B,12) = U_opt[:, 0], the only column the consumer applies (test_MPC.py:196), else
+ * (B,12N).  Arrays as in cmpc_generate_traj / cmpc_solve_host; all pointers host.                              */
+int cmpc_cycle_host(cmpc_handle* h, int B, const double* x0, const double* R_world_to_body, const double* foot_lever,
+                    const double* cmd, const double* t0, double* pos_des, const double* I_world, const double* mass,
+                    double dt, double gait_hz, double duty, const double phase_offset[4], const double hip_offset[12],
+                    int warm, int first_step_only, double* u, int32_t* status, int32_t* iters);
+
+/* Per-QP statistics (B, CMPC_NSTAT) of the last cmpc_solve_host / cmpc_cycle_host call, copied to the host. */
 int cmpc_host_stats(cmpc_handle* h, int B, double* stats_host);
 
 /* Number of kernels launched by this library since process start (bench.py "gpu_launches"). */

@@ -40,7 +40,9 @@ def check_batch(mod, rec, n_oracle, **kw):
     status = sol["status"].cpu().numpy()
     st = sol["stats"].cpu().numpy()
     assert (status == 1).all(), np.unique(status, return_counts=True)
-    assert st[:, 0].max() < 1e-8 and st[:, 1].max() < 1e-7                    # primal / dual residual of every QP
+    fb = np.isin(st[:, 7], (2, 3))                    # the condensed kernel's ADMM fallback stops at its 1e-6 tolerance
+    assert st[~fb, 0].max() < 1e-8 and st[~fb, 1].max() < 1e-7               # primal / dual residual of every exact QP
+    assert fb.mean() < 1e-3 and (not fb.any() or (st[fb, 0].max() < 1e-3 and st[fb, 1].max() < 1e-3))
     u = sol["u"]                                                             # (B,12,N)
     N, B = rec.N, rec.B
     ct = torch.from_numpy(records.host_contact_table(rec.t0, rec.dt, N, rec.gait_hz, rec.duty)).cuda()
@@ -132,3 +134,35 @@ def test_host_entry_equals_device_entry_multichunk(mod, N, stress):
         u, st, it = mpc.solve_host(rec.x0, rec.x_ref, rec.r_foot, rec.I_world, rec.mass, rec.t0, rec.dt, rec.gait_hz, rec.duty)
         assert (st.numpy() == 1).all()
         assert np.abs(u.numpy() - ua)[exact].max() < 1e-9, rep
+
+
+@pytest.mark.parametrize("first_only", [False, True])
+def test_cycle_host_matches_device_pipeline(mod, first_only):
+    """cmpc_cycle_host (408 bytes in per robot, trajectory generated on the device, optionally only U_opt[:, 0] out --
+    test_MPC.py:173-196) against generate_traj -> solve_QP on device tensors: same forces, same carried position target."""
+    from convex_mpc_b200 import com_trajectory as ct
+    B, N, HZ, DUTY = 20000, 16, 3.0, 0.6
+    g = records.random_cycle_inputs(B, 2027)
+    gait = ct.Gait(HZ, DUTY)
+    dt = gait.gait_period / N
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    state = ct.RobotState(d(g["x0"]), d(g["R_wb"]), d(g["lever"]), d(g["mass"]), d(g["I_world"]))
+    traj = ct.ComTraj(state, hip_offset=g["hip"], device="cuda:0")
+    traj.pos_des_world.copy_(d(g["pos_des"]))
+    traj.generate_traj(state, gait, d(g["t0"]), *[d(g["cmd"][:, i]) for i in range(4)], dt)
+    mpc = mod.CentroidalMPC(None, traj, verbose=False, max_stance=40)
+    sol = mpc.solve_QP(None, traj)
+    u_dev = mpc._u.cpu().numpy()
+    host = mod.CentroidalMPC(None, traj, verbose=False, max_stance=40, max_batch=B)
+    pos_des = g["pos_des"].copy()
+    u, st, it = host.cycle_host(g["x0"], g["R_wb"], g["lever"], g["cmd"], g["t0"], pos_des, g["I_world"], g["mass"], dt, g["hip"],
+                                gait_hz=HZ, duty=DUTY, first_step_only=first_only)
+    u, st = u.numpy(), st.numpy()
+    assert (st == 1).all() and (sol["status"].cpu().numpy() == 1).all()
+    assert np.array_equal(pos_des, traj.pos_des_world.cpu().numpy())
+    ref = u_dev[:, :12] if first_only else u_dev
+    assert u.shape == ref.shape and np.abs(u - ref).max() < 1e-9
+    # a second, warm-started cycle through the host entry keeps working from the state left on the device
+    u2, st2, _ = host.cycle_host(g["x0"], g["R_wb"], g["lever"], g["cmd"], g["t0"], pos_des, g["I_world"], g["mass"], dt, g["hip"],
+                                 gait_hz=HZ, duty=DUTY, first_step_only=first_only)
+    assert (st2.numpy() == 1).all() and np.abs(u2.numpy() - ref).max() < 1e-6
