@@ -24,6 +24,7 @@ PROTOTYPES = {
                                 c_double, c_double, c_double, c_int, c_int, c_int, c_int]),
     "cmpc_set_max_stance": (c_int, [c_void_p, c_int]),
     "cmpc_set_generic": (c_int, [c_void_p, c_int]),
+    "cmpc_leg_jacobian": (c_int, [c_int, c_int, c_void_p, c_void_p, c_dp, c_void_p, c_void_p, c_void_p]),
     "cmpc_set_profile": (c_int, [c_void_p, c_int]),
     "cmpc_last_kernel_ms": (c_int, [c_void_p, c_dp, c_dp]),
     "cmpc_set_prepass": (c_int, [c_void_p, c_int]),

@@ -152,6 +152,8 @@ class CentroidalMPC:
       max_stance  upper bound on stance foot-steps per robot (see cmpc_set_max_stance)
       prepass     pre-pass ahead of the condensed kernel: 0 off, 1/2/3 = Riccati sweeps for nominal robots, 4 (default) =
                   wrench-space projected Riccati + primal-dual active set for all robots (cmpc_set_prepass)
+      warm_shift  warm start from the previous working set shifted by one horizon stage (the cycle advances by
+                  about one dt) instead of the unshifted previous solution the reference re-uses (centroidal_mpc.py:108-110)
       generic_kernel  diagnostics: solve raw-input batches with the generic kernel (the one that serves
                   caller-supplied Ad/Bd/gd) instead of the closed-form fast kernel
     """
@@ -159,7 +161,7 @@ class CentroidalMPC:
     def __init__(self, go2, traj, *, device=None, mode="active_set", dynamics="auto", max_batch=None,
                  eps_abs=None, eps_rel=None, max_iter=None, polish=None, check_termination=None,
                  adaptive_rho_interval=None, rho0=1e-4, sigma=1e-6, alpha=1.6, mu=MU, fz_min=FZ_MIN,
-                 Q=None, R=None, max_stance=None, generic_kernel=False, prepass=4, verbose=True):
+                 Q=None, R=None, max_stance=None, generic_kernel=False, prepass=4, warm_shift=False, verbose=True):
         if not torch.cuda.is_available():
             raise _lib.CmpcError("CentroidalMPC needs a CUDA device (no CPU fallback)")
         self._lib = _lib.load()
@@ -197,6 +199,7 @@ class CentroidalMPC:
         if generic_kernel:
             check(self._lib.cmpc_set_generic(self._h, 1))
         check(self._lib.cmpc_set_prepass(self._h, int(prepass)))
+        self._warm_code = 2 if warm_shift else 1
         self._state_B = None
         self._warm = False
         self._warm_host = 0
@@ -421,7 +424,7 @@ class CentroidalMPC:
             self._ev[0].record()
             check(self._lib.cmpc_solve(
                 self._h, B, p("Ad"), p("Bd"), p("gd"), p("x0"), p("x_ref"), p("r_foot"), p("I_world"), p("mass"),
-                float(t.get("dt", 0.0)), self._mask.data_ptr(), int(self._warm),
+                float(t.get("dt", 0.0)), self._mask.data_ptr(), self._warm_code if self._warm else 0,
                 self._u.data_ptr(), self._y.data_ptr(), self._rho.data_ptr(), self._X.data_ptr(),
                 self._nu.data_ptr(), self._status.data_ptr(), self._iters.data_ptr(), self._stats.data_ptr(),
                 stream))
@@ -478,7 +481,7 @@ class CentroidalMPC:
             p = lambda k: t[k].data_ptr() if k in t else None
             check(self._lib.cmpc_solve(
                 self._h, B, p("Ad"), p("Bd"), p("gd"), p("x0"), p("x_ref"), p("r_foot"), p("I_world"), p("mass"),
-                float(t.get("dt", 0.0)), self._mask.data_ptr(), int(self._warm),
+                float(t.get("dt", 0.0)), self._mask.data_ptr(), self._warm_code if self._warm else 0,
                 self._u.data_ptr(), self._y.data_ptr(), self._rho.data_ptr(), self._X.data_ptr(),
                 self._nu.data_ptr(), self._status.data_ptr(), self._iters.data_ptr(), self._stats.data_ptr(), s))
         self._keep = t

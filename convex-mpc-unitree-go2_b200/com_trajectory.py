@@ -153,6 +153,28 @@ def srb_step(state, traj, u, mpc_period, I_body, stance_offset, out=None, stream
     return out
 
 
+GO2_LINKS = (0.0955, 0.213, 0.213)       # abduction offset, thigh, calf (m): the published Go2 leg geometry
+
+
+def leg_jacobian(q_joint, R_world_to_body, links=GO2_LINKS, with_foot_pos=False, stream=None):
+    """World-aligned translational foot Jacobians (B,4,3,3) over each leg's hip / thigh / calf joints from the joint
+    angles ``q_joint`` (B,12; legs FL FR RL RR) and the base orientation -- the analytic counterpart of
+    ``PinGo2Model.compute_3x3_foot_Jacobian_world`` (go2_robot_data.py:286-300), ``cmpc_leg_jacobian``.  With
+    ``with_foot_pos`` also the feet relative to their hips in the body frame (B,4,3)."""
+    lib = _lib.load()
+    dev = q_joint.device
+    B = q_joint.shape[0]
+    q = _dev(q_joint, dev, (B, 12))
+    R = _dev(R_world_to_body, dev, (B, 3, 3))
+    J = torch.empty(B, 4, 3, 3, dtype=torch.float64, device=dev)
+    p = torch.empty(B, 4, 3, dtype=torch.float64, device=dev) if with_foot_pos else None
+    s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.cmpc_leg_jacobian(dev.index or 0, B, q.data_ptr(), R.data_ptr(), _lib.darr(links), J.data_ptr(),
+                                         p.data_ptr() if p is not None else None, ctypes.c_void_p(s)))
+    return (J, p) if with_foot_pos else J
+
+
 def stance_torque(J_foot_world, u, time_now, gait, N, tau_max=45.0, phase_offset=PHASE_OFFSET, stream=None):
     """tau = clip(J^T (-f), +-tau_max) for the legs in stance at ``time_now``, zero for swing legs -- the stance
     branch of ``LegController.compute_leg_torque`` (leg_controller.py:100-101) plus the motor saturation of

@@ -417,6 +417,16 @@ __global__ void stance_torque_kernel(int B, int N, const double* __restrict__ J,
     if (mask_now) mask_now[e] = st;
 }
 
+// Analytic foot Jacobians (cmpc_traj.cuh): one thread per (robot, leg); legs FL FR RL RR, left legs have side = +1.
+__global__ void leg_jacobian_kernel(int B, const double* __restrict__ q, const double* __restrict__ R_wb, double l1, double l2,
+                                    double l3, double* __restrict__ J, double* __restrict__ p_body) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 4 * B) return;
+    const int b = e >> 2, leg = e & 3;
+    traj::leg_jacobian(q + (size_t)b * 12 + 3 * leg, R_wb + (size_t)b * 9, (leg & 1) ? -1.0 : 1.0, l1, l2, l3,
+                       J + (size_t)e * 9, p_body ? p_body + (size_t)e * 3 : nullptr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Roofline denominators: dependent-free DFMA streams and shared-memory 8-byte reads.
 // ---------------------------------------------------------------------------------------------
@@ -858,6 +868,20 @@ int cmpc_stance_torque(int device, int N, int B, const double* J_foot_world, con
     stance_torque_kernel<<<(total + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(
         B, N, J_foot_world, u, time_now, period, duty, phase_offset[0], phase_offset[1], phase_offset[2], phase_offset[3],
         tau_max, tau, mask_now);
+    ++g_launches;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int cmpc_leg_jacobian(int device, int B, const double* q_joint, const double* R_world_to_body, const double link[3],
+                      double* J_foot_world, double* foot_pos_body, void* stream) {
+    if (!q_joint || !R_world_to_body || !link || !J_foot_world) return fail("null argument");
+    if (B < 0) return fail("negative batch");
+    if (B == 0) return 0;
+    CU_TRY(cudaSetDevice(device));
+    const int tpb = 128, total = 4 * B;
+    leg_jacobian_kernel<<<(total + tpb - 1) / tpb, tpb, 0, (cudaStream_t)stream>>>(B, q_joint, R_world_to_body, link[0], link[1], link[2],
+                                                                                 J_foot_world, foot_pos_body);
     ++g_launches;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -175,5 +175,29 @@ CMPC_HD void stance_torque_leg(const double* J, const double* f, int stance, dou
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Analytic leg kinematics of the Go2: the world-aligned translational foot Jacobian over the three
+// joints of a leg, what compute_3x3_foot_Jacobian_world (go2_robot_data.py:286-300) reads out of Pinocchio.  Chain of the
+// Go2 description: hip (abduction) joint about x at the hip position, thigh joint about y at (0, s l1, 0) (s = +1 left, -1
+// right legs), calf joint about y at (0, 0, -l2), foot at (0, 0, -l3); the hip frames are parallel to the body frame, so
+//     p = Rx(q1) [ X, s l1, Z ],   X = -l2 sin q2 - l3 sin(q2+q3),   Z = -l2 cos q2 - l3 cos(q2+q3)
+// is the foot relative to its hip in the body frame and J_world = R_body_to_world dp/dq.  Rb = R_world_to_body (row-major,
+// as go2_robot_data.py:216 hands it out), so R_body_to_world = Rb'.
+// ----------------------------------------------------------------------------------------------
+CMPC_HD void leg_jacobian(const double* q3, const double* Rb, double side, double l1, double l2, double l3, double* Jw, double* p_body) {
+    const double s1 = sin(q3[0]), c1 = cos(q3[0]), s2 = sin(q3[1]), c2 = cos(q3[1]);
+    const double s23 = sin(q3[1] + q3[2]), c23 = cos(q3[1] + q3[2]);
+    const double X = -l2 * s2 - l3 * s23, Z = -l2 * c2 - l3 * c23, y1 = side * l1;
+    if (p_body) { p_body[0] = X; p_body[1] = y1 * c1 - Z * s1; p_body[2] = y1 * s1 + Z * c1; }
+    // dp/dq in the body frame, column j = joint j;  dX/dq2 = Z, dZ/dq2 = -X, dX/dq3 = -l3 c23, dZ/dq3 = l3 s23
+    double Jb[9];
+    Jb[0] = 0.0;                  Jb[1] = Z;        Jb[2] = -l3 * c23;
+    Jb[3] = -y1 * s1 - Z * c1;    Jb[4] = X * s1;   Jb[5] = -l3 * s23 * s1;
+    Jb[6] = y1 * c1 - Z * s1;     Jb[7] = -X * c1;  Jb[8] = l3 * s23 * c1;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            Jw[i * 3 + j] = Rb[0 * 3 + i] * Jb[0 * 3 + j] + Rb[1 * 3 + i] * Jb[1 * 3 + j] + Rb[2 * 3 + i] * Jb[2 * 3 + j];
+}
+
 }  // namespace traj
 }  // namespace cmpc

@@ -331,8 +331,11 @@ CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int 
             if (st) {
                 c = 0;
                 if (warm) {
-                    const double* yf = yo + 12 * N + 16 * k + 4 * q;
-                    const int az = yo[12 * k + 3 * q + 2] < 0.0;
+                    // warm = 1: the previous working set as it is (the reference re-uses its raw previous solution,
+                    // centroidal_mpc.py:92-95,108-110); warm = 2: shifted by one stage (the cycle advanced by about one dt)
+                    const int ks = (warm == 2 && k + 1 < N) ? k + 1 : k;
+                    const double* yf = yo + 12 * N + 16 * ks + 4 * q;
+                    const int az = yo[12 * ks + 3 * q + 2] < 0.0;
                     const int ax = yf[0] > 0.0 ? 1 : (yf[1] > 0.0 ? 2 : 0);
                     const int ay = yf[2] > 0.0 ? 1 : (yf[3] > 0.0 ? 2 : 0);
                     c = (unsigned char)(az | (ax << 1) | (ay << 3));

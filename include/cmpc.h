@@ -132,6 +132,17 @@ int cmpc_srb_step(int device, int N, int B, const double* x, const double* u, co
                   const double stance_offset[12], double* x_out, double* R_world_to_body_out, double* I_world_out,
                   double* foot_lever_out, void* stream);
 
+/* Analytic Go2 leg kinematics: the world-aligned 3 x 3 translational foot Jacobians over each
+ * leg's hip / thigh / calf joints that compute_3x3_foot_Jacobian_world (go2_robot_data.py:286-300) reads out of Pinocchio,
+ * from the joint angles and the base orientation -- the input of cmpc_stance_torque.  Device arrays:
+ *   q_joint (B,12) joint angles, legs FL FR RL RR x (hip, thigh, calf);  R_world_to_body (B,3,3) row-major
+ *   (go2_robot_data.py:216);  link (3) host = abduction offset l1, thigh length l2, calf length l3 (Go2: 0.0955, 0.213,
+ *   0.213 m);  J_foot_world (B,4,3,3) out, row-major, column j = joint j;  foot_pos_body (B,4,3) out or NULL: foot
+ *   relative to its hip in the body frame.  The URDF is not in the reference tree: the chain is the published Go2
+ *   geometry (hip about x, thigh and calf about y), checked against finite differences of its own forward kinematics. */
+int cmpc_leg_jacobian(int device, int B, const double* q_joint, const double* R_world_to_body, const double link[3],
+                      double* J_foot_world, double* foot_pos_body, void* stream);
+
 /* Stance torque mapping, the step after the path: for every leg in stance at time_now
  * (Gait.compute_current_mask, gait.py:21-24, bit-exact)  tau = clip(J^T (-f), -tau_max, tau_max)  with f the
  * first-step force of the MPC (leg_controller.py:100-101, test_MPC.py:196,227); swing legs get 0 (their torque is
@@ -169,7 +180,8 @@ int cmpc_build(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
 
 /* CentroidalMPC.solve_QP (centroidal_mpc.py:69-120): build + solve, fused, one CTA per robot.
  * Inputs as in cmpc_build plus mask (B,W).  In/out warm-start state: u (B,12N), y (B,28N), rho (B)
- * (warm != 0 -> use them as the initial guess, as centroidal_mpc.py:92-95 does).
+ * (warm != 0 -> use them as the initial guess, as centroidal_mpc.py:92-95 does; warm = 2: the working set of the
+ * previous solution shifted by one horizon stage, SURVEY.md section 8 f4 -- the reference does not shift, :108-110).
  * Optional outputs (may be NULL): X (B,12N), nu (B,12N).  status (B) int32, iters (B) int32,
  * stats (B, CMPC_NSTAT).                                                                         */
 int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const double* gd,

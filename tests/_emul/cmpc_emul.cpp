@@ -207,6 +207,14 @@ int emul_wrench(const Params* p, int B, int N, int nfmax, const double* x0, cons
     return 0;
 }
 
+int emul_leg_jacobian(int B, const double* q, const double* R_wb, const double* link, double* J, double* p_body) {
+    for (int b = 0; b < B; ++b)
+        for (int leg = 0; leg < 4; ++leg)
+            traj::leg_jacobian(q + (size_t)b * 12 + 3 * leg, R_wb + (size_t)b * 9, (leg & 1) ? -1.0 : 1.0, link[0], link[1], link[2],
+                               J + ((size_t)b * 4 + leg) * 9, p_body ? p_body + ((size_t)b * 4 + leg) * 3 : nullptr);
+    return 0;
+}
+
 size_t emul_ws_bytes_fast(int N, int nfmax) {
     fast::WsF w;
     return fast::ws_carve_fast(w, reinterpret_cast<unsigned char*>(4096), N, nfmax, nullptr);

@@ -156,6 +156,14 @@ class Emul:
                               _p(u), _p(y), _p(rho), _p(X), _p(nu), _p(st), _p(it), _p(stats), _p(done))
         return dict(u=u, y=y, rho=rho, X=X, nu=nu, status=st, iters=it, stats=stats, mask=mask, done=done)
 
+    def leg_jacobian(self, q, R_wb, link):
+        """traj::leg_jacobian (csrc/cmpc_traj.cuh) on the host: (J (B,4,3,3), foot_pos_body (B,4,3))."""
+        q = np.ascontiguousarray(q, dtype=np.float64); R_wb = np.ascontiguousarray(R_wb, dtype=np.float64)
+        B = q.shape[0]
+        J = np.zeros((B, 4, 3, 3)); pb = np.zeros((B, 4, 3))
+        self.lib.emul_leg_jacobian(B, _p(q), _p(R_wb), _p(np.asarray(link, dtype=np.float64)), _p(J), _p(pb))
+        return J, pb
+
     def wrench(self, rec, mask=None, nfmax=None, warm=0, state=None, **kw):
         """Wrench-space projected Riccati + PDAS (csrc/cmpc_wrench.cuh); ``done`` marks the robots it finished,
         ``sweeps`` the Riccati sweeps it ran."""

@@ -49,10 +49,13 @@ def check_batch(mod, rec, n_oracle, **kw):
     f = u.reshape(B, 4, 3, N)
     swing = (ct == 0)
     assert float(f.abs().amax(dim=2)[swing].max()) == 0.0                   # centroidal_mpc.py:150-161
-    fz = f[:, :, 2, :][~swing]
-    assert float(fz.min()) >= 10.0 - 1e-8                                    # :163-170
-    assert float((f[:, :, 0, :].abs()[~swing] - 0.8 * fz).max()) <= 1e-8     # :324-359
-    assert float((f[:, :, 1, :].abs()[~swing] - 0.8 * fz).max()) <= 1e-8
+    # feasibility per robot: exact paths to 1e-8, the few ADMM-fallback robots to their 1e-3 N stop (tolerance 1e-2 N)
+    tol = torch.from_numpy(np.where(fb, 1e-3, 1e-8)).cuda()[:, None, None]
+    big = torch.full_like(f[:, :, 2, :], 1e9)
+    fz = f[:, :, 2, :]
+    assert bool(((torch.where(swing, big, fz) - 10.0) >= -tol).all())        # :163-170
+    for c in (0, 1):                                                         # :324-359
+        assert bool((torch.where(swing, -big, f[:, :, c, :].abs() - 0.8 * fz) <= tol).all())
     un = u.cpu().numpy()
     worst = 0.0
     for b in np.linspace(0, B - 1, n_oracle).astype(int):

@@ -398,6 +398,31 @@ def test_stance_torque_mapping(mod):
     assert (np.abs(tau) == 45.0).any() and (tau.reshape(B, 4, 3)[ref_mask == 0] == 0).all()
 
 
+def test_leg_jacobian_feeds_the_stance_torque(mod):
+    """cmpc_leg_jacobian (the analytic counterpart of compute_3x3_foot_Jacobian_world,
+    go2_robot_data.py:286-300) against the oracle's axis-cross-lever Jacobian, then tau = clip(J^T (-f)) through
+    cmpc_stance_torque (leg_controller.py:100-101)."""
+    from convex_mpc_b200 import com_trajectory as ct
+    from oracle import leg_kin
+    rng = np.random.default_rng(21)
+    B, N = 4096, 16
+    q = np.stack([rng.uniform(-0.8, 0.8, (B, 4)), rng.uniform(-0.5, 2.0, (B, 4)), rng.uniform(-2.6, -0.9, (B, 4))], axis=2).reshape(B, 12)
+    R = records._rot_zyx(rng.normal(0, 0.2, B), rng.normal(0, 0.2, B), rng.uniform(-np.pi, np.pi, B))
+    R_wb = np.ascontiguousarray(np.swapaxes(R, 1, 2))
+    J, pb = ct.leg_jacobian(dev(q), dev(R_wb), with_foot_pos=True)
+    J, pb = J.cpu().numpy(), pb.cpu().numpy()
+    for b in range(0, B, 37):
+        for leg in range(4):
+            q3 = q[b, 3 * leg:3 * leg + 3]
+            assert np.abs(J[b, leg] - leg_kin.jacobian_world(q3, R_wb[b], leg_kin.SIDE[leg])).max() < 1e-14
+            assert np.abs(pb[b, leg] - leg_kin.foot_pos_body(q3, leg_kin.SIDE[leg])).max() < 1e-14
+    u = rng.normal(0, 60, (B, 12 * N)); u[:, 2:12:3] = np.abs(u[:, 2:12:3]) + 30
+    t_now = rng.uniform(0, 50, B)
+    tau, mask = ct.stance_torque(dev(J), dev(u), dev(t_now), ct.Gait(3.0, 0.6), N, tau_max=45.0)
+    ref = np.clip(np.einsum("blij,bli->blj", J, -u[:, :12].reshape(B, 4, 3)), -45.0, 45.0) * mask.cpu().numpy()[:, :, None]
+    assert np.abs(tau.cpu().numpy().reshape(B, 4, 3) - ref).max() < 1e-12
+
+
 def test_drop_in_single_robot_api(mod):
     """The reference call pattern (test_MPC.py:153-192) with un-batched NumPy fields and Ad/Bd/gd."""
     rec = records.random_records(1, seed=9, stress=1.0)

@@ -200,3 +200,32 @@ def test_tighter_stance_bound_keeps_the_working_set_capacity(emul):
         fz_rows = sum(abs(y[12 * k + 3 * leg + 2]) > 1e-9 for k in range(rec.N) for leg in range(4) if ct[leg, k])
         rows.append(int(fz_rows + (np.abs(y[12 * rec.N:]) > 1e-9).sum()))
     assert max(r for r, path in zip(rows, a["stats"][:, 7]) if path == 1) > 64, rows
+
+
+def test_leg_jacobian_source_against_oracle_and_finite_differences():
+    """traj::leg_jacobian (the device source, compiled for the host) against oracle/leg_kin.py (joint axis x lever, a
+    different derivation) and against central differences of the oracle's link-by-link forward kinematics -- the
+    analytic counterpart of compute_3x3_foot_Jacobian_world (go2_robot_data.py:286-300)."""
+    from oracle import leg_kin
+    from convex_mpc_b200 import records
+    rng = np.random.default_rng(3)
+    B = 64
+    q = np.stack([rng.uniform(-0.8, 0.8, (B, 4)), rng.uniform(-0.5, 2.0, (B, 4)), rng.uniform(-2.6, -0.9, (B, 4))], axis=2).reshape(B, 12)
+    R = records._rot_zyx(rng.normal(0, 0.2, B), rng.normal(0, 0.2, B), rng.uniform(-np.pi, np.pi, B))
+    R_wb = np.ascontiguousarray(np.swapaxes(R, 1, 2))
+    J, pb = Emul().leg_jacobian(q, R_wb, leg_kin.GO2_LINKS)
+    h = 1e-6
+    for b in range(B):
+        for leg in range(4):
+            q3 = q[b, 3 * leg:3 * leg + 3]
+            side = leg_kin.SIDE[leg]
+            assert np.abs(pb[b, leg] - leg_kin.foot_pos_body(q3, side)).max() < 1e-15
+            Jo = leg_kin.jacobian_world(q3, R_wb[b], side)
+            assert np.abs(J[b, leg] - Jo).max() < 1e-15
+            fd = np.stack([(leg_kin.foot_pos_body(q3 + h * e, side) - leg_kin.foot_pos_body(q3 - h * e, side)) / (2 * h)
+                           for e in np.eye(3)], axis=1)
+            assert np.abs(J[b, leg] - R_wb[b].T @ fd).max() < 1e-9
+    # nominal stance (hip 0, thigh 0.9, calf -1.8): the foot is under the thigh joint, 0.0955 m out from the hip
+    _, p0 = Emul().leg_jacobian(np.tile([0.0, 0.9, -1.8], 4)[None], np.eye(3)[None], leg_kin.GO2_LINKS)
+    assert np.abs(p0[0, :, 0]).max() < 1e-15 and np.allclose(p0[0, :, 1], [0.0955, -0.0955, 0.0955, -0.0955])
+    assert np.allclose(p0[0, :, 2], -2 * 0.213 * np.cos(0.9))

@@ -2,7 +2,11 @@
     generate_traj -> contact table + solve_QP (warm-started) -> srb_step
 all on the GPU (cmpc_generate_traj, cmpc_contact_table, cmpc_solve, cmpc_srb_step); the host only enqueues.
 
-    python tools/closed_loop.py [B=1024] [cycles=500] [out=gpurun_out/closed_loop.json]
+    python tools/closed_loop.py [B=1024] [cycles=500] [out=gpurun_out/closed_loop.json] [shift]
+
+``shift``: warm start from the previous working set shifted by one horizon stage instead of the
+unshifted previous solution.  With CMPC_PREPASS_MIN_BATCH=1 the Riccati-sweep kernel also serves batches below 2 048
+robots; ``sweeps_mean_sampled`` then tells how many sweeps a warm-started cycle needs.
 """
 import json
 import os
@@ -18,6 +22,7 @@ from convex_mpc_b200.centroidal_mpc import CentroidalMPC  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 OUT = sys.argv[3] if len(sys.argv) > 3 else os.path.join("gpurun_out", "closed_loop.json")
+SHIFT = len(sys.argv) > 4 and sys.argv[4] == "shift"
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(1024)
 HZ, DUTY, N, MPC_DT = 3.0, 0.6, 16, 0.02
@@ -43,7 +48,8 @@ cmd = [t(rng.uniform(-0.8, 0.8, B)), t(rng.uniform(-0.4, 0.4, B)), t(np.full(B, 
 
 traj = ct.ComTraj(state, hip_offset=hip, device=dev)
 traj.generate_traj(state, gait, 0.0, *cmd, dt)
-mpc = CentroidalMPC(None, traj, verbose=False, max_stance=40)
+mpc = CentroidalMPC(None, traj, verbose=False, max_stance=40, warm_shift=SHIFT)
+sweeps = []
 nxt = None
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 solved = 0
@@ -61,12 +67,16 @@ for c in range(C + WARM):
     if c >= WARM and (c % 50 == 0 or c == C + WARM - 1):
         st = sol["stats"].cpu().numpy(); nchecks += 1
         solved += int((sol["status"].cpu().numpy() == 1).sum()); worst_rp = max(worst_rp, st[:, 0].max()); worst_rd = max(worst_rd, st[:, 1].max())
-        paths += np.bincount(st[:, 7].astype(int), minlength=5)[:5]
+        paths += np.bincount(st[:, 7].astype(int), minlength=6)[:5]
+        rs = np.isin(st[:, 7].astype(int), (4, 5))
+        if rs.any():
+            sweeps.append(float(1 + st[rs, 6].mean()))
 ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1])
 xf = state.x.cpu().numpy()
 res = {"robots": B, "cycles": C, "ms_total": ms, "ms_per_cycle": ms / C, "cycles_per_s": C / ms * 1e3, "qps_per_s": B * C / ms * 1e3,
-       "checked_cycles_all_solved": bool(solved == B * nchecks),
+       "checked_cycles_all_solved": bool(solved == B * nchecks), "warm_shift": SHIFT,
+       "sweeps_mean_sampled": float(np.mean(sweeps)) if sweeps else None,
        "r_prim_max": worst_rp, "r_dual_max": worst_rd, "paths_sampled": paths.tolist(),
        "height_mean": float(xf[:, 2].mean()), "height_min": float(xf[:, 2].min()), "speed_mean": float(np.linalg.norm(xf[:, 6:8], axis=1).mean()),
        "note": "eager: includes the Python enqueue overhead of three C-ABI calls + solution dict per cycle and solve_QP's two stream synchronisations"}
