@@ -237,6 +237,47 @@ def next_cycle(rec, u_first, mpc_period=0.02):
     return Records(x_new, x_ref, r_foot, I_world, rec.mass, t0, dt, rec.gait_hz, rec.duty, N)
 
 
+def retarget(rec, vx_body, vy_body, yaw_rate):
+    """New command for every robot of ``rec`` (the piecewise-constant schedule of test_MPC.py:37-47): the reference window is
+    rebuilt from the current state the way ``ComTraj.generate_traj`` does (com_trajectory.py:84-103), body-frame velocity
+    rotated by the current yaw."""
+    N, dt = rec.N, rec.dt
+    yaw = rec.x0[:, 5]
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    v = np.stack([c * vx_body - s_ * vy_body, s_ * vx_body + c * vy_body, np.zeros_like(yaw)], axis=1)
+    tv = (np.arange(N) + 1) * dt
+    x_ref = np.zeros_like(rec.x_ref)
+    pos = rec.x0[:, 0:3].copy(); pos[:, 2] = 0.27
+    x_ref[:, 0:3, :] = pos[:, :, None] + v[:, :, None] * tv[None, None, :]
+    x_ref[:, 5, :] = yaw[:, None] + yaw_rate * tv[None, :]
+    x_ref[:, 6:9, :] = v[:, :, None]
+    x_ref[:, 11, :] = yaw_rate
+    return Records(rec.x0, x_ref, rec.r_foot, rec.I_world, rec.mass, rec.t0, rec.dt, rec.gait_hz, rec.duty, N)
+
+
+# ------------------------------------------------------------------------------------------------
+# Recorded-states replay format (BASELINE configs[1], SURVEY.md section 8d config #2): one .npz holds C cycles of B robots,
+# every array with a leading cycle axis -- x0 (C,B,12), x_ref (C,B,12,N), r_foot (C,B,4,3,N), I_world (C,B,3,3), mass (C,B),
+# t0 (C,B) -- plus dt, gait_hz, duty, N and, optionally, the forces a solver returned (u (C,B,12N)) for later comparison.
+# The reference keeps the same per-cycle quantities in Python lists for its plots (test_MPC.py:100-131).
+# ------------------------------------------------------------------------------------------------
+def save_cycles(path, cycles, u=None):
+    first = cycles[0]
+    arrs = {k: np.stack([getattr(c, k) for c in cycles]) for k in ("x0", "x_ref", "r_foot", "I_world", "mass", "t0")}
+    if u is not None:
+        arrs["u"] = np.stack(u)
+    np.savez_compressed(path, dt=first.dt, gait_hz=first.gait_hz, duty=first.duty, N=first.N, **arrs)
+
+
+def load_cycles(path):
+    """(list of Records, recorded forces (C,B,12N) or None)."""
+    z = np.load(path)
+    C = z["x0"].shape[0]
+    cyc = [Records(z["x0"][c], z["x_ref"][c], z["r_foot"][c], z["I_world"][c], z["mass"][c], z["t0"][c], float(z["dt"]),
+                   float(z["gait_hz"]), float(z["duty"]), int(z["N"])) for c in range(C)]
+    return cyc, (z["u"] if "u" in z.files else None)
+
+
 def srb_step_host(x, u_first, x_ref, r_foot, I_world, mass, T, I_body=GO2_I_BODY, stance_offset=None):
     """NumPy twin of ``cmpc_srb_step`` (csrc/cmpc_traj.cuh): the MPC's own single-rigid-body model
     (com_trajectory.py:234-270) held for ``T`` seconds under the first-step forces (exact ZOH, A_c^2 = 0).

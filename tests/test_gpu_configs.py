@@ -169,3 +169,17 @@ def test_cycle_host_matches_device_pipeline(mod, first_only):
     u2, st2, _ = host.cycle_host(g["x0"], g["R_wb"], g["lever"], g["cmd"], g["t0"], pos_des, g["I_world"], g["mass"], dt, g["hip"],
                                  gait_hz=HZ, duty=DUTY, first_step_only=first_only)
     assert (st2.numpy() == 1).all() and np.abs(u2.numpy() - ref).max() < 1e-6
+
+
+def test_config1_record_and_replay(mod, tmp_path):
+    """BASELINE configs[1] in miniature: 64 robots x 12 closed-loop cycles recorded to the .npz replay format
+    (records.save_cycles), then replayed in order, warm-started: the same forces come back."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import replay as rp
+    path = str(tmp_path / "replay_64x12.npz")
+    cyc, us = rp.record(64, 12, path)
+    back, u_back = records.load_cycles(path)
+    assert len(back) == 12 and back[0].B == 64 and np.array_equal(back[5].x_ref, cyc[5].x_ref) and np.array_equal(u_back[7], us[7])
+    res = rp.replay(path, str(tmp_path / "replay.json"))
+    assert res["max_abs_force_difference_to_recording_N"] < 1e-6
