@@ -243,15 +243,16 @@ def retarget(rec, vx_body, vy_body, yaw_rate):
     rotated by the current yaw."""
     N, dt = rec.N, rec.dt
     yaw = rec.x0[:, 5]
+    vx_body, vy_body, yaw_rate = (np.broadcast_to(np.asarray(a, dtype=np.float64), yaw.shape) for a in (vx_body, vy_body, yaw_rate))
     c, s_ = np.cos(yaw), np.sin(yaw)
     v = np.stack([c * vx_body - s_ * vy_body, s_ * vx_body + c * vy_body, np.zeros_like(yaw)], axis=1)
     tv = (np.arange(N) + 1) * dt
     x_ref = np.zeros_like(rec.x_ref)
     pos = rec.x0[:, 0:3].copy(); pos[:, 2] = 0.27
     x_ref[:, 0:3, :] = pos[:, :, None] + v[:, :, None] * tv[None, None, :]
-    x_ref[:, 5, :] = yaw[:, None] + yaw_rate * tv[None, :]
+    x_ref[:, 5, :] = yaw[:, None] + yaw_rate[:, None] * tv[None, :]
     x_ref[:, 6:9, :] = v[:, :, None]
-    x_ref[:, 11, :] = yaw_rate
+    x_ref[:, 11, :] = yaw_rate[:, None]
     return Records(rec.x0, x_ref, rec.r_foot, rec.I_world, rec.mass, rec.t0, rec.dt, rec.gait_hz, rec.duty, N)
 
 
@@ -266,7 +267,7 @@ def save_cycles(path, cycles, u=None):
     arrs = {k: np.stack([getattr(c, k) for c in cycles]) for k in ("x0", "x_ref", "r_foot", "I_world", "mass", "t0")}
     if u is not None:
         arrs["u"] = np.stack(u)
-    np.savez_compressed(path, dt=first.dt, gait_hz=first.gait_hz, duty=first.duty, N=first.N, **arrs)
+    np.savez(path, dt=first.dt, gait_hz=first.gait_hz, duty=first.duty, N=first.N, **arrs)
 
 
 def load_cycles(path):
