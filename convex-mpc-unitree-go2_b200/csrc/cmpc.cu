@@ -325,7 +325,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
     const int max_it = p.pdas_max_iter;
     int b = -1, it = 0, nst = 0;
     bool exhausted = false;
-    wr::Policy pl{0, false};
+    wr::Policy pl = wr::policy_init();
     for (;;) {
         const bool need = (b < 0) && !exhausted;
         int nb = -1;
@@ -333,7 +333,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         nb = __shfl_sync(0xffffffffu, nb, lane & ~3);
         bool fresh = false;
         if (need) {
-            if (nb < B) { b = nb; it = 0; pl = wr::Policy{0, false}; fresh = true; e.b = b; }
+            if (nb < B) { b = nb; it = 0; pl = wr::policy_init(); fresh = true; e.b = b; }
             else exhausted = true;
         }
         if (!__any_sync(0xffffffffu, b >= 0)) break;
@@ -344,12 +344,12 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
         unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
         const double pmin = wr::backward_sweep(qlane, ts, sh, e, cur);
-        const int fl = wr::forward_sweep(qlane, valid, ts, sh, e, cur, next, it, wr::policy_damp(it));
+        const int fl = wr::forward_sweep(qlane, valid, ts, sh, e, cur, next, it, wr::policy_damp(pl, it));
         if (valid && !(pmin > 0.0)) fail = true;
         bool single = false;
-        const int ps = wr::policy_step(pl, fl, it, max_it, single);       // working-set policy (block updates, damping, cycle breakers)
+        const int ps = wr::policy_step(pl, fl, it, max_it, N <= 16, single);       // working-set policy (block updates, damping, cycle breakers)
         const bool conv = valid && !fail && ps == 1;
-        if (valid && !conv && it + 1 >= max_it + wr::kBlockExtra + wr::kSingleMax) fail = true;
+        if (valid && !conv && (ps == 2 || it + 1 >= max_it + wr::kBlockExtra + wr::kSingleMax)) fail = true;
         if (__any_sync(0xffffffffu, conv)) {
             const int ok = wr::finish_robot(qlane, conv, ts, sh, e, cur, warm, nst, it + 1);
             if (conv && !ok) fail = true;

@@ -97,7 +97,7 @@ struct TS {
     double ax[3];            // forward: block a of A x_k ; finish: co-state block
     double red[4];           // finish: partial reductions
     D2 gk[GAIN_D2];          // forward: gains of the current stage (loaded one stage ahead)
-    int chg;
+    int chg, nact;           // forward: changed foot-steps; rows of the next working set (this thread's foot)
     unsigned hsh;            // forward: running hash of this thread's part of the next working set
     double dworst, amost;    // forward: single-exchange candidates of this thread's foot (most negative multiplier, largest violation)
     int didx, aidx;
@@ -613,7 +613,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 // forward sweep: states, forces, multipliers, next working set.  Writes forces / stance duals / states to the output
 // arrays when `valid`.  Returns bit 0: the working set changed, bit 1: the new set is one of the last eight (a cycle;
 // `it` = sweeps done before this one = valid entries of the history), bit 2: there is a single-exchange candidate,
-// bits 8 and up: the number of foot-steps whose working set changed.
+// bits 8-15: the number of foot-steps whose working set changed, bits 16 and up: rows of the next working set.
 // ------------------------------------------------------------------------------------------------------------------
 // With `damp` the block update is one-sided on every other foot-step: rows whose multiplier is negative leave the working
 // set only where k + foot + it is even (violated rows always join).  Dropping half of the candidates per sweep is what
@@ -632,7 +632,7 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     const double* x0 = e.bt->x0 + (size_t)e.b * 12;
 #pragma unroll
     for (int i = 0; i < 3; ++i) t.pv[i] = x0[3 * q + i];
-    t.chg = 0; t.hsh = 2166136261u;
+    t.chg = 0; t.nact = 0; t.hsh = 2166136261u;
     t.dworst = -tol; t.amost = 1e-9; t.didx = -1; t.aidx = -1;
     ring_issue(q, sh, e, 0);
     const D2* g = e.gains + WR_GQ;
@@ -731,6 +731,7 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
         next[4 * k + q] = nc;
         t.chg += (nc != code);
         t.hsh = (t.hsh ^ nc) * 16777619u;
+        if (nc != SWING) t.nact += (nc & 1) + ((nc >> 1) & 3 ? 1 : 0) + ((nc >> 3) & 3 ? 1 : 0);
         if (valid) {
             double* uo = out_u(e) + 12 * k + 3 * q;
             double* yo = out_y(e);
@@ -766,14 +767,15 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
     double* cand = sh->E1 + 60;           // 4 x (value of the drop candidate, value of the add candidate)
     int* candi = reinterpret_cast<int*>(sh->E1 + 68);
     WR_Q_BEGIN
-    sh->flag[q] = t.chg;
+    sh->flag[q] = t.chg | (t.nact << 12);
     sh->hq[q] = t.hsh;
     cand[2 * q] = t.dworst; cand[2 * q + 1] = t.amost;
     candi[2 * q] = t.didx; candi[2 * q + 1] = t.aidx;
     WR_Q_END
     WR_SYNC();
-    const int nchg = sh->flag[0] + sh->flag[1] + sh->flag[2] + sh->flag[3];
-    res = (nchg > 0 ? 1 : 0) | (nchg << 8);
+    const int fsum = sh->flag[0] + sh->flag[1] + sh->flag[2] + sh->flag[3];
+    const int nchg = fsum & 0xfff, nact = fsum >> 12;
+    res = (nchg > 0 ? 1 : 0) | ((nchg > 255 ? 255 : nchg) << 8) | (nact << 16);
     // (a damped update depends on the parity of the sweep, so the same set at the other parity is not a repetition)
     const unsigned H = sh->hq[0] * 0x9E3779B1u + sh->hq[1] * 0x85EBCA77u + sh->hq[2] * 0xC2B2AE3Du + sh->hq[3] * 0x27D4EB2Fu +
                        ((damp && (it & 1)) ? 0x165667B1u : 0u);
@@ -973,6 +975,7 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, co
 
 constexpr int kSingleMax = 8;        // single exchanges after the block budget before the robot is handed to the condensed kernel
 constexpr int kBreakMax = 6;         // one-off single exchanges (cycle breakers) before the robot stays in single-exchange mode
+constexpr int kHandOffIter = 6, kHandOffRows = 12;
 constexpr int kDampAfter = 8;        // block updates are one-sided on every other foot-step from this sweep on
 constexpr int kBlockExtra = 12;      // block updates: pdas_max_iter + kBlockExtra sweeps (damped updates of disturbed robots take up to ~20)
 
@@ -982,16 +985,25 @@ constexpr int kBlockExtra = 12;      // block updates: pdas_max_iter + kBlockExt
 // 9-20 sweeps instead of not at all.  A working set that comes back (hash history, any period up to 8) is moved off the
 // cycle by ONE single exchange (most negative multiplier out, else most violated row in); after kBreakMax such breaks, or
 // when the block budget is spent, single exchanges only.
-// fl: flags of forward_sweep.  Returns 1 = converged, 0 = go on; `single` tells which update to apply.
-struct Policy { int nbreak; bool latched; };
-CMPC_HD bool policy_damp(int it) { return it >= kDampAfter; }
-CMPC_HD int policy_step(Policy& pl, int fl, int it, int max_it, bool& single) {
+// fl: flags of forward_sweep.  Returns 1 = converged, 0 = go on, 2 = hand over to the condensed kernel; `single` tells which
+// update to apply.
+struct Policy { int nbreak; bool latched; int damp_from; };
+CMPC_HD Policy policy_init() { return Policy{0, false, kDampAfter}; }
+CMPC_HD bool policy_damp(const Policy& pl, int it) { return it >= pl.damp_from; }
+CMPC_HD int policy_step(Policy& pl, int fl, int it, int max_it, bool handoff, bool& single) {
     single = pl.latched;
-    if (pl.latched || policy_damp(it)) { if (!(fl & 4)) return 1; }      // nothing to exchange: the Karush-Kuhn-Tucker conditions hold
+    const bool damped = policy_damp(pl, it);
+    if (pl.latched || damped) { if (!(fl & 4)) return 1; }      // nothing to exchange: the Karush-Kuhn-Tucker conditions hold
     else if (!(fl & 1)) return 1;
     if (pl.latched) return 0;
+    // a lightly constrained robot that is still moving rows after kHandOffIter sweeps (0.06 % of the nominal workload: cycles
+    // of period 3-5) costs the condensed kernel ~60 us but would keep its warp alive for several more sweeps at the end of
+    // the batch: hand it over.  Heavily constrained robots stay (the condensed kernel needs milliseconds for those).
+    // Only where the condensed kernel keeps its factor in shared memory (N <= 16): at N = 32 / 48 it costs milliseconds too.
+    if (handoff && it + 1 >= kHandOffIter && (fl >> 16) <= kHandOffRows) return 2;
     const bool budget = it + 1 >= max_it + kBlockExtra;
     if (((fl & 1) && (fl & 2)) || budget) {
+        if (!damped && !budget) { pl.damp_from = it + 1; return 0; }      // first answer to a cycle: damp the updates from now on
         single = true;
         if (++pl.nbreak > kBreakMax || budget) pl.latched = true;
         if (!(fl & 4)) return 1;
@@ -1008,17 +1020,18 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
     if (sweeps_out) *sweeps_out = 0;
     if (nst == 0 || nst > nfmax || (N & 3)) return 0;     // lever arms are fetched four stages at a time
     const int max_it = e.p->pdas_max_iter;
-    Policy pl{0, false};
+    Policy pl = policy_init();
     for (int it = 0; it < max_it + kBlockExtra + kSingleMax; ++it) {
         const unsigned char* cur = codes + (size_t)(it % 3) * 4 * N;
         unsigned char* next = codes + (size_t)((it + 1) % 3) * 4 * N;
         const double pmin = backward_sweep(qlane, ts, sh, e, cur);
         if (!(pmin > 0.0)) return 0;
-        const int fl = forward_sweep(qlane, true, ts, sh, e, cur, next, it, policy_damp(it));
+        const int fl = forward_sweep(qlane, true, ts, sh, e, cur, next, it, policy_damp(pl, it));
         if (sweeps_out) *sweeps_out = it + 1;
         bool single;
-        const int ps = policy_step(pl, fl, it, max_it, single);
+        const int ps = policy_step(pl, fl, it, max_it, N <= 16, single);
         if (ps == 1) return finish_robot(qlane, true, ts, sh, e, cur, warm, nst, it + 1);
+        if (ps == 2) return 0;
         single_step(qlane, single, ts, sh, cur, next, N);
     }
     return 0;
