@@ -1132,10 +1132,21 @@ int cmpc_solve_host(cmpc_handle* h, int B, const double* x0, const double* x_ref
     // the first copy in and the last copy out cannot hide behind anything: ramp the chunk size up from 4 096
     // (4096, 8192, then `chunk`) and finish with a 4 096-robot chunk, so that only small transfers are exposed
     const bool ramp = (B >= 8 * chunk) && !getenv("CMPC_HOST_CHUNK");
+    // tuning: an explicit chunk schedule, e.g. CMPC_HOST_CHUNKS=16384,32768,16384 (the last entry repeats)
+    int sched[16], nsched = 0;
+    if (const char* e = getenv("CMPC_HOST_CHUNKS")) {
+        const char* q_ = e;
+        while (*q_ && nsched < 16) { const int v = atoi(q_); if (v >= 256) sched[nsched++] = v; while (*q_ && *q_ != ',') ++q_; if (*q_ == ',') ++q_; }
+    } else if (B >= 65536 && !getenv("CMPC_HOST_CHUNK")) {
+        // a small first chunk lets the kernels start early, a small last one shortens the copy out that nothing can hide
+        // (measured at 65 536 robots, tools/host_path_probe.py: 8192,24576,24576,8192 -> 6.4 ms; two halves 7.0; four quarters 7.8)
+        sched[0] = B / 8; sched[1] = 3 * (B / 8); sched[2] = 3 * (B / 8); sched[3] = B - sched[0] - sched[1] - sched[2]; nsched = 4;
+    }
     int ci = 0, nb = 0, rc = 0;
     for (int lo = 0; lo < B && !rc; lo += nb, ++ci) {
         int want = chunk;
-        if (ramp) {
+        if (nsched) want = sched[ci < nsched ? ci : nsched - 1];
+        else if (ramp) {
             if (ci == 0) want = 4096;
             else if (ci == 1) want = 8192;
             const int rem = B - lo;

@@ -67,4 +67,14 @@ for chunk in (0, 4096, 8192, 16384, 32768, 65536):
         m.solve_host(*hb, rec.dt, rec.gait_hz, rec.duty, out=out)
     res[f"solve_host_chunk_{chunk or 'default'}_ms"] = timeit(step)
     del m
+os.environ.pop("CMPC_HOST_CHUNK", None)
+for sch in ("16384,32768,16384", "8192,16384,32768,8192", "16384,16384,16384,16384", "8192,24576,24576,8192", "21846,21845,21845", "12288,40960,12288"):
+    os.environ["CMPC_HOST_CHUNKS"] = sch
+    m = CentroidalMPC(None, traj, verbose=False, max_stance=ms_, max_batch=B)
+
+    def step():
+        m._warm_host = 0
+        m.solve_host(*hb, rec.dt, rec.gait_hz, rec.duty, out=out)
+    res[f"solve_host_sched_{sch}_ms"] = timeit(step)
+    del m
 print(json.dumps(res, indent=1))
