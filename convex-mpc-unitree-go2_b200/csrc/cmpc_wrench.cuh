@@ -423,7 +423,7 @@ CMPC_HD double backward_sweep(int qlane, TS* ts, Sh* sh, const Env& e, const uns
 #pragma unroll
             for (int i = 0; i < 6; ++i) wh[i] = 0.0;
             const double* rg = ring_at(sh, k);
-#pragma unroll
+#pragma unroll 1          // rolled on purpose: the stage body is instruction-fetch bound (17 % of the warp samples wait for instructions)
             for (int j = 0; j < 4; ++j) {
                 const FootP f = foot_proj(cur[4 * k + j], j, tb, p.mu, p.fz_min);
                 const double r3[3] = {rg[(3 * j) * 4], rg[(3 * j + 1) * 4], rg[(3 * j + 2) * 4]};
