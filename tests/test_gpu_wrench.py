@@ -102,3 +102,28 @@ def test_warm_start_from_previous_duals(mod):
     assert (mpc._status.cpu().numpy() == 1).all()
     assert np.abs(u2 - a["u"])[ok].max() < 1e-7
     assert (st[ok, 6] == 0).mean() > 0.99
+
+
+def test_shifted_warm_start_same_optimum(mod):
+    """warm_shift=True (the previous working set shifted by one horizon stage; the reference re-uses the
+    unshifted previous solution, centroidal_mpc.py:108-110) is only a different first guess: the next cycle's optimum is
+    the cold-start optimum, and the closed-loop successor of a batch needs no more sweeps than with the unshifted guess."""
+    rec = records.random_records(4096, seed=31, stress=0.2)
+    _, _, cold0 = solve(mod, rec, prepass=4)
+    nxt = records.next_cycle(rec, cold0["u"][:, :12])
+    _, _, cold = solve(mod, nxt, prepass=4)
+    sweeps = {}
+    for shift in (False, True):
+        traj0 = mod.BatchedComTraj.from_records(rec, device="cuda:0")
+        traj1 = mod.BatchedComTraj.from_records(nxt, device="cuda:0")
+        mpc = mod.CentroidalMPC(None, traj0, verbose=False, prepass=4, warm_shift=shift)
+        mpc.solve_QP(None, traj0)
+        mpc.solve_QP(None, traj1)                 # warm
+        torch.cuda.synchronize()
+        st = mpc._stats.cpu().numpy()
+        assert (mpc._status.cpu().numpy() == 1).all()
+        ok = np.isin(st[:, 7], (4, 5)) & np.isin(cold["stats"][:, 7], (4, 5))
+        assert ok.mean() > 0.99
+        assert np.abs(mpc._u.cpu().numpy() - cold["u"])[ok].max() < 1e-6
+        sweeps[shift] = float(1 + st[ok, 6].mean())
+    assert sweeps[True] <= sweeps[False] + 0.05, sweeps
