@@ -127,3 +127,21 @@ def test_shifted_warm_start_same_optimum(mod):
         assert np.abs(mpc._u.cpu().numpy() - cold["u"])[ok].max() < 1e-6
         sweeps[shift] = float(1 + st[ok, 6].mean())
     assert sweeps[True] <= sweeps[False] + 0.05, sweeps
+
+
+@pytest.mark.parametrize("N", [18, 20])
+def test_horizons_off_the_four_stage_grid(mod, N):
+    """The Riccati route fetches lever arms four stages at a time, so it serves horizons that are multiples of 4 (N = 20);
+    any other horizon (N = 18) takes the round-1 route (lock-step pre-pass + condensed kernel).  Same exact optimum either way."""
+    rec = records.random_records(2048, N=N, seed=900 + N, stress=0.2)
+    _, _, a = solve(mod, rec, prepass=4)
+    assert (a["status"] == 1).all()
+    path = a["stats"][:, 7].astype(int)
+    if N % 4 == 0:
+        assert np.isin(path, (4, 5)).mean() > 0.99 and (path == 5).any()
+    else:
+        assert not (path == 5).any() and (path == 4).any()
+    for i in list(np.flatnonzero(path != 4)[:3]) + list(np.flatnonzero(path == 4)[:2]):
+        sol = oracle_solution(rec, i)
+        err, rel = force_error(a["u"][i], sol["sol"]["U"])
+        assert err < 1e-6, (i, err)
