@@ -350,13 +350,26 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
         const int ps = wr::policy_step(pl, fl, it, max_it, N <= 16, single);       // working-set policy (block updates, damping, cycle breakers)
         const bool conv = valid && !fail && ps == 1;
         if (valid && !conv && (ps == 2 || it + 1 >= max_it + wr::kBlockExtra + wr::kSingleMax)) fail = true;
-        if (__any_sync(0xffffffffu, conv)) {
-            const int ok = wr::finish_robot(qlane, conv, ts, sh, e, cur, warm, nst, it + 1);
-            if (conv && !ok) fail = true;
-        }
+        wr::mark_pending(qlane, conv, e, nst, it + 1);      // the certificate kernel takes it from here
         wr::single_step(qlane, single && valid && !conv && !fail, ts, sh, cur, next, N);
         if (fail && qlane == 0) worklist[atomicAdd(ctl, 1)] = b;
         if ((conv && !fail) || fail) b = -1; else if (valid) ++it;
+    }
+}
+
+// Certificates and remaining outputs of the robots the sweep kernel settled (cmpc_wrench.cuh, certify_group): sixteen lanes
+// per robot, nothing carried over from the sweeps -- everything is recomputed from X, u, y.  Robots whose certificate does not
+// hold join the work-list of the condensed kernel.
+__global__ void __launch_bounds__(256)
+wrench_certificate_kernel(Params p, wr::Bat bt, int B, int warm, int* __restrict__ worklist, int* __restrict__ ctl) {
+    const int lane = threadIdx.x & 31, gl = lane & 15;
+    const unsigned gmask = 0xFFFFu << (lane & 16);
+    const int per = blockDim.x >> 4;
+    for (int base = blockIdx.x * per; base < B; base += gridDim.x * per) {
+        const int b = base + (threadIdx.x >> 4);
+        if (b >= B || bt.status[b] != wr::ST_PENDING) continue;          // uniform inside the group of sixteen
+        const int ok = wr::certify_group(gl, gmask, p, bt, b, warm);
+        if (!ok && gl == 0) worklist[atomicAdd(ctl, 1)] = b;
     }
 }
 
@@ -553,7 +566,7 @@ struct cmpc_handle {
     size_t yg_stride = 0, hp_stride = 0, hp_stride_generic = 0;
     size_t reserved_bytes = 0;
     // cudaFuncSetAttribute is issued only when the dynamic shared-memory size of a kernel changes
-    size_t attr_fast[2] = {0, 0}, attr_generic = 0, attr_build = 0, attr_ric[3] = {0, 0, 0}, attr_wrench = 0;
+    size_t attr_fast[2] = {0, 0}, attr_generic = 0, attr_build = 0, attr_ric[3] = {0, 0, 0}, attr_wrench = 0, attr_cert = 0;
     // device-resident state for the *_host entry
     struct HostPath {
         bool ready = false;
@@ -1010,6 +1023,10 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                     wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W};
                     wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bt, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
                                                                          sl.worklist, sl.ctl, wr::robot_bytes(h->N));
+                    ++g_launches;
+                    CU_TRY(cudaGetLastError());
+                    const int want_c = (B + 15) / 16, cap_c = h->sm_count * 64;
+                    wrench_certificate_kernel<<<want_c < cap_c ? want_c : cap_c, 256, 0, st>>>(h->p, bt, B, warm, sl.worklist, sl.ctl);
                     launched = true;
                 }
             }

@@ -33,6 +33,7 @@ namespace cmpc {
 namespace wr {
 
 enum { PATH_WRENCH = 5 };
+enum { ST_PENDING = 3 };         // internal marker: working set settled by the sweep kernel, certificate kernel to follow
 constexpr unsigned char SWING = 255;
 constexpr int GAIN_D2 = 10;      // double2 slots per thread and stage: Ktil rows (9), kbar part (1)
 
@@ -973,6 +974,17 @@ CMPC_HD int finish_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, co
     return ok;
 }
 
+// Device route: the sweep kernel only marks a settled robot; wrench_certificate_kernel (cmpc.cu, certify_group below) forms
+// the certificate and the remaining outputs for all settled robots of the batch at full memory parallelism.
+CMPC_HD void mark_pending(int qlane, bool conv, const Env& e, int nst, int sweeps) {
+    if (conv && qlane == 0) {
+        e.bt->status[e.b] = ST_PENDING;
+        double* st = out_stats(e);
+        st[3] = (double)(3 * nst);
+        st[6] = (double)(sweeps - 1);
+    }
+}
+
 constexpr int kSingleMax = 8;        // single exchanges after the block budget before the robot is handed to the condensed kernel
 constexpr int kBreakMax = 6;         // one-off single exchanges (cycle breakers) before the robot stays in single-exchange mode
 constexpr int kHandOffIter = 6, kHandOffRows = 12;
@@ -1036,6 +1048,168 @@ CMPC_HD int solve_robot(int qlane, TS* ts, Sh* sh, const Env& e, int nfmax, int 
     }
     return 0;
 }
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------------------------------
+// Certificate of one settled robot by SIXTEEN lanes (lane l owns the stages l, l + 16, l + 32): co-states, stationarity and
+// feasibility from first principles -- X, u, y as the last forward sweep wrote them, independent of the factorizations --
+// and the remaining outputs in the reference's layouts; the same quantities as finish_robot (the host emulation's
+// version).  A = I + dt E with E^2 = 0, so the co-state recursion nu_k = A'nu_{k+1} - 2 Q (x_{k+1} - xref_k) has the closed
+// form  nu_k[p, rpy] = -2 S_k,  nu_k[v, omega] = -2 S_k + dt Rz' sum_{j > k} nu_j[p, rpy]  with suffix sums S over the
+// stages: two suffix scans over the sixteen lanes instead of a sequential sweep, and every global access is coalesced
+// across the lanes.  Returns (to every lane) 1 if the certificate holds.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double grp_suffix_sum(double v, unsigned gmask, int gl) {       // inclusive, from lane gl up to 15
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const double t = __shfl_down_sync(gmask, v, o, 16);
+        if (gl + o < 16) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ double grp_max(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gmask, v, o, 16));
+    return v;
+}
+__device__ __forceinline__ double grp_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, 16);
+    return v;
+}
+__device__ inline int certify_group(int gl, unsigned gmask, const Params& p, const Bat& bt, int b, int warm) {
+    const int N = bt.N;
+    const double dt = bt.dt, h = dt * dt / 2.0;
+    const double* __restrict__ xr = bt.x_ref + (size_t)b * 12 * N;
+    const double* __restrict__ rf = bt.r_foot + (size_t)b * 12 * N;
+    const double* __restrict__ Xo = bt.X + (size_t)b * 12 * N;
+    const double* __restrict__ uo = bt.u + (size_t)b * 12 * N;
+    double* yo = bt.y + (size_t)b * 28 * N;
+    const uint64_t* mk = bt.mask ? bt.mask + (size_t)b * bt.W : nullptr;
+    // constants of the robot (every lane; the loads are broadcasts)
+    double cst[12];
+    {
+        double sum = 0.0;
+        for (int k = gl; k < N; k += 16) sum += xr[(size_t)5 * N + k];
+        const double yaw = grp_sum(sum, gmask) / (double)N;
+        DynCommon dc;
+        dyn_common(dc, xr, 0, bt.I_world + (size_t)b * 9, bt.mass[b], dt);        // N = 0: yaw is formed above
+        cst[0] = cos(yaw); cst[1] = sin(yaw); cst[2] = dc.minv;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cst[3 + i] = dc.Iinv[i];
+    }
+    const double cy = cst[0], sy = cst[1];
+    double rd = 0.0, rp = 0.0, obj = 0.0, na = 0.0;
+    double carry0[12], carry1[6];          // suffix sums of the chunks above this one: S (12) and sum of nu[p, rpy] (6)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) carry0[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) carry1[i] = 0.0;
+    const int nchunk = (N + 15) >> 4;
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+        const int k = ch * 16 + gl;
+        const bool act = k < N;
+        const int kk = act ? k : N - 1;
+        double S[12], nu[12];
+        // everything the stage reads, up front: one round of memory latency per chunk
+        double xr12[12], x12[12], f12[12], r12[12], yb4[4], yf16[16];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { xr12[i] = xr[(size_t)i * N + kk]; r12[i] = rf[(size_t)i * N + kk]; }
+        {
+            const double2* xp = reinterpret_cast<const double2*>(Xo + 12 * kk);
+            const double2* up = reinterpret_cast<const double2*>(uo + 12 * kk);
+            const double2* yp = reinterpret_cast<const double2*>(yo + 12 * N + 16 * kk);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { const double2 a = xp[i], c2 = up[i]; x12[2 * i] = a.x; x12[2 * i + 1] = a.y; f12[2 * i] = c2.x; f12[2 * i + 1] = c2.y; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const double2 a = yp[i]; yf16[2 * i] = a.x; yf16[2 * i + 1] = a.y; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yb4[j] = yo[12 * kk + 3 * j + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double r = xr12[i];
+            const double dd = x12[i] - r;
+            const double qe = act ? p.Q[i] * dd : 0.0;
+            obj += act ? p.Q[i] * (dd * dd - r * r) : 0.0;
+            S[i] = grp_suffix_sum(qe, gmask, gl) + carry0[i];
+        }
+        // nu[p, rpy] = -2 S;  T = sum_{j > k} nu_j[p, rpy] = (inclusive suffix sum of nu) - nu_k
+        double T[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            nu[i] = -2.0 * S[i];
+            T[i] = grp_suffix_sum(act ? nu[i] : 0.0, gmask, gl) + carry1[i] - (act ? nu[i] : 0.0);
+        }
+        nu[6] = -2.0 * S[6] + dt * T[0];
+        nu[7] = -2.0 * S[7] + dt * T[1];
+        nu[8] = -2.0 * S[8] + dt * T[2];
+        nu[9] = -2.0 * S[9] + dt * (cy * T[3] - sy * T[4]);
+        nu[10] = -2.0 * S[10] + dt * (sy * T[3] + cy * T[4]);
+        nu[11] = -2.0 * S[11] + dt * T[5];
+        // carries for the chunk below: totals of this chunk (lane 0 holds the inclusive sums over the whole chunk)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) carry0[i] = __shfl_sync(gmask, S[i], 0, 16);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) carry1[i] = __shfl_sync(gmask, T[i] + nu[i], 0, 16);
+        if (act) {
+            if (bt.nu) {
+                double2* no = reinterpret_cast<double2*>(bt.nu + (size_t)b * 12 * N + 12 * k);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) no[i] = make_double2(nu[2 * i], nu[2 * i + 1]);
+            }
+            double bn[6];
+            bbar_t(cst, dt, h, nu, bn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double r3[3] = {r12[3 * j], r12[3 * j + 1], r12[3 * j + 2]};
+                double W[9], s3[3];
+                foot_W(cst + 3, r3, W);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s3[c] = bn[c] + W[c] * bn[3] + W[3 + c] * bn[4] + W[6 + c] * bn[5];
+                if (mask_bit(mk, N, j, k)) {
+                    const double* f = f12 + 3 * j;
+                    const double l0 = -yb4[j];
+                    const double y0 = yf16[4 * j], y1 = yf16[4 * j + 1], y2 = yf16[4 * j + 2], y3 = yf16[4 * j + 3];
+                    const double atl[3] = {y0 - y1, y2 - y3, -l0 - p.mu * (y0 + y1 + y2 + y3)};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        rd = fmax(rd, fabs(2.0 * p.R[3 * j + c] * f[c] - s3[c] + atl[c]));
+                        obj += p.R[3 * j + c] * f[c] * f[c];
+                    }
+                    rp = fmax(rp, fmax(p.fz_min - f[2], fmax(fabs(f[0]), fabs(f[1])) - p.mu * f[2]));
+                    na += (l0 > 0.0) + (y0 > 0.0) + (y1 > 0.0) + (y2 > 0.0) + (y3 > 0.0);
+                    rd = fmax(rd, fmax(fmax(-l0, -y0), fmax(fmax(-y1, -y2), -y3)));      // multipliers must not be negative
+                    yo[12 * k + 3 * j] = 0.0;
+                    yo[12 * k + 3 * j + 1] = 0.0;
+                } else {
+                    yo[12 * k + 3 * j] = s3[0];
+                    yo[12 * k + 3 * j + 1] = s3[1];
+                    yo[12 * k + 3 * j + 2] = s3[2];
+                }
+            }
+        }
+    }
+    rd = grp_max(rd, gmask); rp = grp_max(rp, gmask); obj = grp_sum(obj, gmask); na = grp_sum(na, gmask);
+    const int ok = (rd <= 1e-6) && (rp <= 1e-9);
+    if (ok && gl == 0) {
+        double* rho_p = bt.rho ? bt.rho + b : nullptr;
+        const double rho = (warm && rho_p && *rho_p > 0.0) ? *rho_p : p.rho0;
+        if (rho_p) *rho_p = rho;
+        double* st = bt.stats + (size_t)b * NSTAT;
+        const int sweeps = (int)st[6] + 1;
+        bt.status[b] = ST_SOLVED;
+        bt.iters[b] = 0;
+        st[0] = fmax(rp, 0.0);
+        st[1] = rd;
+        st[2] = obj;
+        st[4] = na;
+        st[5] = rho;
+        st[7] = (double)(sweeps > 1 ? (int)PATH_WRENCH : (int)PATH_RICCATI);
+    }
+    return ok;
+}
+#endif
 
 CMPC_HD void fill_tab(Tab& tb, const Params& p, int i) {
     // entry i of the tables (i < 12: Q, R, Rinv; i < 16: sig)
