@@ -398,13 +398,13 @@ def main():
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
-    kern_ms, k_pre, k_con = [], [], []
-    a_ms, b_ms = ctypes.c_double(), ctypes.c_double()
+    kern_ms, k_pre, k_cert, k_con = [], [], [], []
+    a_ms, b_ms, c_ms = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
     for i in range(args.steps):
         step()
         kern_ms.append(mpc.kernel_ms)
-        if lib.cmpc_last_kernel_ms(mpc._h, ctypes.byref(a_ms), ctypes.byref(b_ms)) == 0:
-            k_pre.append(a_ms.value); k_con.append(b_ms.value)
+        if lib.cmpc_last_kernel_ms3(mpc._h, ctypes.byref(a_ms), ctypes.byref(c_ms), ctypes.byref(b_ms)) == 0:
+            k_pre.append(a_ms.value); k_cert.append(c_ms.value); k_con.append(b_ms.value)
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop()
@@ -423,6 +423,7 @@ def main():
     kms = float(np.mean(kern_ms))
     pre_ms = float(np.mean(k_pre)) if k_pre else None
     con_ms = float(np.mean(k_con)) if k_con else None
+    cert_ms = float(np.mean(k_cert)) if k_cert else None
 
     # ---- end-to-end through the host-buffer C-ABI call ------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -514,6 +515,19 @@ def main():
             kernels.append({"name": pre_name, "ms": pre_ms, "algorithmic_flops": f_pre,
                             "achieved": f_pre / (pre_ms * 1e-3) / 1e12, "frac": f_pre / (pre_ms * 1e-3) / 1e12 / f64.value,
                             "robots_finished": int(np.isin(stats[:, 7].astype(int), (4, 5)).sum())})
+        if args.prepass == 4 and cert_ms:
+            # the certificate pass: 0.7 kFLOP per stage and robot (roofline.py), HBM-bound rather than FP64-bound: X, u, y, x_ref,
+            # r_foot in (76 N doubles), co-states and box rows of y out (24 N doubles) per robot
+            nfin = int(np.isin(stats[:, 7].astype(int), (4, 5)).sum())
+            f_cert = nfin * N * 0.7e3
+            b_cert = nfin * 8.0 * (76 * N + 24 * N)
+            kernels[-1]["algorithmic_flops"] = f_pre - f_cert
+            kernels[-1]["achieved"] = (f_pre - f_cert) / (pre_ms * 1e-3) / 1e12
+            kernels[-1]["frac"] = kernels[-1]["achieved"] / f64.value
+            kernels.append({"name": "wrench_certificate_kernel", "ms": cert_ms, "algorithmic_flops": f_cert,
+                            "achieved": f_cert / (cert_ms * 1e-3) / 1e12, "frac": f_cert / (cert_ms * 1e-3) / 1e12 / f64.value,
+                            "bound": "hbm", "algorithmic_bytes": b_cert, "hbm_gbs": b_cert / (cert_ms * 1e-3) / 1e9,
+                            "hbm_frac": b_cert / (cert_ms * 1e-3) / 1e9 / hbm_peak, "robots_finished": nfin})
         if con_ms is not None:
             kernels.append({"name": "solve_fast_kernel", "ms": con_ms, "algorithmic_flops": f_con,
                             "achieved": f_con / (max(con_ms, 1e-6) * 1e-3) / 1e12,

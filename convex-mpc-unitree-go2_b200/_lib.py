@@ -27,6 +27,7 @@ PROTOTYPES = {
     "cmpc_leg_jacobian": (c_int, [c_int, c_int, c_void_p, c_void_p, c_dp, c_void_p, c_void_p, c_void_p]),
     "cmpc_set_profile": (c_int, [c_void_p, c_int]),
     "cmpc_last_kernel_ms": (c_int, [c_void_p, c_dp, c_dp]),
+    "cmpc_last_kernel_ms3": (c_int, [c_void_p, c_dp, c_dp, c_dp]),
     "cmpc_set_prepass": (c_int, [c_void_p, c_int]),
     "cmpc_workspace_bytes": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "cmpc_reserve": (c_int, [c_void_p, c_int]),

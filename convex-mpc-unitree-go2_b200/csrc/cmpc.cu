@@ -360,7 +360,7 @@ wrench_pdas_kernel(Params p, wr::Bat bt, int B, int nfmax, int warm, wr::D2* __r
 // Certificates and remaining outputs of the robots the sweep kernel settled (cmpc_wrench.cuh, certify_group): sixteen lanes
 // per robot, nothing carried over from the sweeps -- everything is recomputed from X, u, y.  Robots whose certificate does not
 // hold join the work-list of the condensed kernel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 wrench_certificate_kernel(Params p, wr::Bat bt, int B, int warm, int* __restrict__ worklist, int* __restrict__ ctl) {
     const int lane = threadIdx.x & 31, gl = lane & 15;
     const unsigned gmask = 0xFFFFu << (lane & 16);
@@ -559,7 +559,7 @@ struct cmpc_handle {
     std::atomic<unsigned> slot_next{0};
     // per-kernel timing of cmpc_solve (cmpc_set_profile): events before the pre-pass, between the two kernels and after
     int profile = 0;
-    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};      // before | after the sweep kernel | after the pre-pass | after the condensed kernel
     int pev_valid = 0;
     int reserved_batch = 0;         // robots the slots are sized for (0 = not reserved yet)
     int reserved_nfmax = 0;
@@ -791,11 +791,24 @@ int cmpc_last_kernel_ms(cmpc_handle* h, double* prepass_ms, double* condensed_ms
     if (!h || !prepass_ms || !condensed_ms) return fail("null argument");
     if (!h->profile || !h->pev_valid) return fail("no profiled solve on this handle (cmpc_set_profile, then cmpc_solve with raw inputs)");
     CU_TRY(cudaSetDevice(h->device));
-    CU_TRY(cudaEventSynchronize(h->pev[2]));
+    CU_TRY(cudaEventSynchronize(h->pev[3]));
     float a = 0.f, b = 0.f;
+    CU_TRY(cudaEventElapsedTime(&a, h->pev[0], h->pev[2]));
+    CU_TRY(cudaEventElapsedTime(&b, h->pev[2], h->pev[3]));
+    *prepass_ms = a; *condensed_ms = b;
+    return 0;
+}
+
+int cmpc_last_kernel_ms3(cmpc_handle* h, double* sweep_ms, double* certificate_ms, double* condensed_ms) {
+    if (!h || !sweep_ms || !certificate_ms || !condensed_ms) return fail("null argument");
+    if (!h->profile || !h->pev_valid) return fail("no profiled solve on this handle (cmpc_set_profile, then cmpc_solve with raw inputs)");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaEventSynchronize(h->pev[3]));
+    float a = 0.f, b = 0.f, c = 0.f;
     CU_TRY(cudaEventElapsedTime(&a, h->pev[0], h->pev[1]));
     CU_TRY(cudaEventElapsedTime(&b, h->pev[1], h->pev[2]));
-    *prepass_ms = a; *condensed_ms = b;
+    CU_TRY(cudaEventElapsedTime(&c, h->pev[2], h->pev[3]));
+    *sweep_ms = a; *certificate_ms = b; *condensed_ms = c;
     return 0;
 }
 
@@ -1009,7 +1022,7 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
         const int* wlc = nullptr;
         // small batches are latency-bound (fewer robots than CTA slots x a few rounds): the extra kernel in front only
         // adds to the latency there (batch 1: 45 -> 99 us), so the pre-pass starts at prepass_min_batch robots
-        if (h->profile) { CU_TRY(cudaEventRecord(h->pev[0], st)); CU_TRY(cudaEventRecord(h->pev[1], st)); h->pev_valid = 0; }
+        if (h->profile) { for (int i = 0; i < 3; ++i) CU_TRY(cudaEventRecord(h->pev[i], st)); h->pev_valid = 0; }
         if (h->prepass && h->p.mode == CMPC_MODE_ACTIVE_SET && B >= h->prepass_min_batch) {
             CU_TRY(cudaMemsetAsync(sl.ctl, 0, 4 * sizeof(int), st));
             bool launched = false;
@@ -1025,8 +1038,9 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                                                                          sl.worklist, sl.ctl, wr::robot_bytes(h->N));
                     ++g_launches;
                     CU_TRY(cudaGetLastError());
-                    const int want_c = (B + 15) / 16, cap_c = h->sm_count * 64;
-                    wrench_certificate_kernel<<<want_c < cap_c ? want_c : cap_c, 256, 0, st>>>(h->p, bt, B, warm, sl.worklist, sl.ctl);
+                    if (h->profile) CU_TRY(cudaEventRecord(h->pev[1], st));
+                    const int want_c = (B + 7) / 8, cap_c = h->sm_count * 128;
+                    wrench_certificate_kernel<<<want_c < cap_c ? want_c : cap_c, 128, 0, st>>>(h->p, bt, B, warm, sl.worklist, sl.ctl);
                     launched = true;
                 }
             }
@@ -1076,14 +1090,14 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 wl = sl.worklist; wlc = sl.ctl;
                 const int cap_f = h->sm_count * 2;
                 grid_f = B < cap_f ? B : cap_f;
-                if (h->profile) CU_TRY(cudaEventRecord(h->pev[1], st));
+                if (h->profile) { if (h->prepass != 4) CU_TRY(cudaEventRecord(h->pev[1], st)); CU_TRY(cudaEventRecord(h->pev[2], st)); }
             }
         }
         if (hstride) solve_fast_kernel<true><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, sl.hp, hstride, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
         else solve_fast_kernel<false><<<grid_f, kThreads, smem, st>>>(h->p, bi, bo, B, h->nfmax, warm, nullptr, 0, wl, wlc, sl.yg, yg_stride_of(h, h->nfmax));
         ++g_launches;
         CU_TRY(cudaGetLastError());
-        if (h->profile) { CU_TRY(cudaEventRecord(h->pev[2], st)); h->pev_valid = 1; }
+        if (h->profile) { CU_TRY(cudaEventRecord(h->pev[3], st)); h->pev_valid = 1; }
         return 0;
     }
     const size_t stride = hp_stride_generic(h, h->nfmax);

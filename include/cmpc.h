@@ -93,6 +93,8 @@ int cmpc_set_prepass(cmpc_handle* h, int on);
  * The reference's counterpart are the wall-clock timers of centroidal_mpc.py:102-105. */
 int cmpc_set_profile(cmpc_handle* h, int on);
 int cmpc_last_kernel_ms(cmpc_handle* h, double* prepass_ms, double* condensed_ms);
+/* The same with the pre-pass split into its sweep kernel and its certificate kernel (route 4; otherwise certificate_ms = 0). */
+int cmpc_last_kernel_ms3(cmpc_handle* h, double* sweep_ms, double* certificate_ms, double* condensed_ms);
 
 /* Workspace (section 8b "no allocation inside solve").  A handle keeps four SLOTS of device workspace (work-list,
  * counters, gain scratch, L2-resident scratch of the condensed kernel); consecutive cmpc_solve / cmpc_build calls
