@@ -20,7 +20,7 @@ if [ $rc -eq 0 ]; then
   ncu --set full --clock-control none --import-source on -k "regex:wrench_pdas_kernel" -s 2 -c 1 -f -o $O/${TAG}_prof \
       python tools/prof_case_prepass.py 65536 0.0 40 4 > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-      -k "regex:wrench_pdas_kernel|solve_fast_kernel" -s 4 -c 2 --csv --log-file $O/${TAG}_traffic_65536.csv \
+      -k "regex:wrench_pdas_kernel|wrench_certificate_kernel|solve_fast_kernel" -s 6 -c 3 --csv --log-file $O/${TAG}_traffic_65536.csv \
       python tools/prof_case_prepass.py 65536 0.0 40 4 > $O/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
 fi
 for s in 0.05 0.3; do

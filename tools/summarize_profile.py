@@ -62,7 +62,7 @@ for r in sr[h + 1:]:
         for i in cols: st[sh[i][6:]] += int(r[i] or 0)
 ssum = sum(st.values())
 with open(os.path.join(out, f"{tag}_{kernel}_ncu_summary.txt"), "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on, one launch of {kernel} (tools/prof_case.py 4736 0.0 40)\n")
+    f.write(f"# ncu --set full --clock-control none --import-source on, one launch of {kernel} (tools/prof_case_prepass.py 65536 0.0 40 4: the bench's own size)\n")
     for k, v in m.items(): f.write(f"{k:80s} {v}\n")
     f.write("\n# warp stall reasons, all samples\n")
     for k, v in st.most_common(): f.write(f"stall_{k:24s} {v:8d} {100*v/ssum:5.1f}%\n")
