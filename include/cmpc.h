@@ -192,6 +192,11 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                double* u, double* y, double* rho, double* X, double* nu,
                int32_t* status, int32_t* iters, double* stats, void* stream);
 
+/* Streams: cmpc_solve enqueues on the caller's stream; with the Riccati route (batches >= 2 048) it also forks an internal
+ * stream per workspace slot (the certificate kernel runs there while the condensed kernel serves the hand-overs on the
+ * caller's stream) and joins it back before returning -- everything stays ordered with respect to the caller's stream, and
+ * the fork / join is captured with the rest when the caller's stream is being captured into a CUDA graph. */
+
 /* Same call with HOST buffers (pinned or pageable): chunked H2D -> contact table -> solve -> D2H,
  * copies overlapped with compute on two streams.  Raw-input path only (Ad/Bd computed on device).
  * t0 (B) host.  Outputs u (B,12N), status (B), iters (B) on the host; warm-start state stays
