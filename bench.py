@@ -7,18 +7,22 @@
 Metric (BASELINE.json): MPC QPs solved/sec at horizon N=16, batch 64K per GPU; p50 batch latency.
 Workload: BASELINE configs[2] -- 65 536 randomized Go2 trot states + references per GPU, cold start
 (every step re-solves the batch from scratch; inputs of one batch, 213 MB, exceed the 126 MB L2).
-One "step" = one batched ``solve_QP`` (contact table + dynamics + condensed QP build + solve, fused).
+One "step" = one batched ``solve_QP`` (contact table + dynamics + QP data + exact active-set solve, fused on the device).
 
   value      QPs/s with inputs resident in HBM (CUDA events, barrier + sync on both sides, max over ranks)
   e2e        the same through the host-buffer C-ABI call ``cmpc_solve_host`` (pinned host memory in,
              forces/status out; H2D and D2H inside the timed region)
-  roofline   fused solve kernel vs the FP64-FMA roofline (peak measured on this GPU by the library's
-             DFMA micro-benchmark -- MEASURED_PEAKS.json has no FP64 entry) + achieved HBM GB/s vs
-             MEASURED_PEAKS.json
-  cpu_baseline   the oracle's C port of the reference CPU path (OSQP restatement) on the host cores
+  e2e_cycle  the whole cycle from state + command through ``cmpc_cycle_host`` (trajectory generated on the device,
+             first-step forces out: 408 B in / 96 B out per robot)
+  roofline   the dominant kernel vs the FP64-FMA roofline at the flops of the route every robot took, its duration
+             measured live by CUDA events inside ``cmpc_solve`` (peak measured on this GPU by the library's DFMA
+             micro-benchmark -- MEASURED_PEAKS.json has no FP64 entry); ``kernels`` lists every kernel of the solve,
+             ``hbm`` the achieved HBM GB/s vs MEASURED_PEAKS.json, ``traffic`` the ncu DRAM bytes of the newest capture
+  cpu_baseline   the oracle's C port of the reference CPU path (OSQP restatement) on the host cores, with the
+             CPU-1 / CPU-P warm variants of BASELINE.md section 2, and a sampled L2 check of the GPU forces
 
-``--impl reference`` times that CPU port alone (the reference itself needs CasADi/OSQP/Pinocchio,
-none of which is installable here -- DESIGN.md section 7).
+``--impl reference`` times the reference's own CasADi -> OSQP path when the casadi wheel and the reference tree are
+present (oracle/live_reference.py), else that CPU port alone.
 """
 import argparse
 import ctypes

@@ -68,7 +68,8 @@ for chunk in (0, 4096, 8192, 16384, 32768, 65536):
     res[f"solve_host_chunk_{chunk or 'default'}_ms"] = timeit(step)
     del m
 os.environ.pop("CMPC_HOST_CHUNK", None)
-for sch in ("16384,32768,16384", "8192,16384,32768,8192", "16384,16384,16384,16384", "8192,24576,24576,8192", "21846,21845,21845", "12288,40960,12288"):
+for sch in ("8192,24576,24576,8192", "8192,16384,16384,12288,8192,4096", "8192,20480,20480,8192,4096,4096", "12288,20480,16384,8192,4096,4096",
+            "16384,16384,16384,8192,4096,4096", "8192,24576,16384,8192,4096,4096", "4096,12288,20480,16384,8192,4096"):
     os.environ["CMPC_HOST_CHUNKS"] = sch
     m = CentroidalMPC(None, traj, verbose=False, max_stance=ms_, max_batch=B)
 
