@@ -373,6 +373,19 @@ wrench_certificate_kernel(Params p, wr::Bat bt, int B, int warm, int* __restrict
     }
 }
 
+// Constants of every robot ahead of the sweeps (cy, sy, 1/m, Iinv: what wr::robot_consts forms): one thread per robot, so that
+// the sweep kernel -- four threads per robot, bound by instruction fetch -- carries neither sincos nor N serial loads.
+__global__ void robot_consts_kernel(int B, int N, const double* __restrict__ x_ref, const double* __restrict__ I_world,
+                                    const double* __restrict__ mass, double dt, double* __restrict__ cst) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    DynCommon dc;
+    dyn_common(dc, x_ref + (size_t)b * 12 * N, N, I_world + (size_t)b * 9, mass[b], dt);
+    double* o = cst + (size_t)b * 12;
+    o[0] = dc.cy; o[1] = dc.sy; o[2] = dc.minv;
+    for (int i = 0; i < 9; ++i) o[3 + i] = dc.Iinv[i];
+}
+
 // A head start for the condensed kernel (see cmpc_solve): one thread that lets `cycles` clock ticks pass.
 __global__ void head_start_kernel(long long cycles) {
     const long long t0 = clock64();
@@ -560,6 +573,7 @@ struct cmpc_handle {
         double* yg = nullptr;                                 // rows of large working sets, per CTA of the condensed kernel
         double* hp = nullptr;                                 // block-packed factor when it does not fit shared memory
         double* xs = nullptr;                                 // predicted states (B,12N) when the caller does not ask for them
+        double* cst = nullptr;                                // (B,12) robot constants of route 4
         // route 4: the condensed kernel works on the hand-overs of the sweep kernel on `aux` while the certificate kernel runs;
         // robots whose certificate fails go to a second list (worklist + wl_cap, ctl + 4), served after the join
         size_t wl_cap = 0;
@@ -677,13 +691,13 @@ SlotSizes slot_sizes(const cmpc_handle* h, int B) {
     if (hb > hs) hs = hb;
     z.hp = hs * ctas * sizeof(double);
     z.xs = (size_t)B * 12 * h->N * sizeof(double);
-    z.total = 4 * (z.worklist + z.ctl + z.gains + z.yg + z.hp + z.xs);
+    z.total = 4 * (z.worklist + z.ctl + z.gains + z.yg + z.hp + z.xs + (size_t)B * 12 * sizeof(double));
     return z;
 }
 
 void free_slots(cmpc_handle* h) {
     for (auto& q : h->slot) {
-        void* ptrs[] = {q.worklist, q.ctl, q.gains, q.yg, q.hp, q.xs};
+        void* ptrs[] = {q.worklist, q.ctl, q.gains, q.yg, q.hp, q.xs, q.cst};
         for (void* p : ptrs) if (p) cudaFree(p);
         if (q.aux) cudaStreamDestroy(q.aux);
         if (q.ev_fork) cudaEventDestroy(q.ev_fork);
@@ -708,6 +722,7 @@ int reserve_slots(cmpc_handle* h, int B) {
         if (z.yg) CU_TRY(cudaMalloc(&q.yg, z.yg));
         if (z.hp) CU_TRY(cudaMalloc(&q.hp, z.hp));
         CU_TRY(cudaMalloc(&q.xs, z.xs));
+        CU_TRY(cudaMalloc(&q.cst, (size_t)B * 12 * sizeof(double)));
         q.wl_cap = (size_t)B;
         CU_TRY(cudaStreamCreateWithFlags(&q.aux, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&q.ev_fork, cudaEventDisableTiming));
@@ -1054,7 +1069,9 @@ int cmpc_solve(cmpc_handle* h, int B, const double* Ad, const double* Bd, const 
                 const int grid_w = wrench_grid(h, B);
                 if ((h->N & 3) == 0 && smem_w <= h->smem_optin && (size_t)grid_w * h->N * wr::GAIN_D2 * kWrThreads * sizeof(wr::D2) <= sl.gain_bytes) {
                     if (set_smem((const void*)wrench_pdas_kernel, smem_w, &h->attr_wrench)) return -1;
-                    wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W};
+                    robot_consts_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, h->N, x_ref, I_world, mass, dt, sl.cst);
+                    ++g_launches;
+                    wr::Bat bt{x0, x_ref, r_foot, I_world, mass, mask, u, y, rho, X ? X : sl.xs, nu, stats, status, iters, dt, h->N, h->W, sl.cst};
                     wrench_pdas_kernel<<<grid_w, kWrThreads, smem_w, st>>>(h->p, bt, B, h->nfmax, warm, reinterpret_cast<wr::D2*>(sl.gains),
                                                                          sl.worklist, sl.ctl, wr::robot_bytes(h->N));
                     ++g_launches;

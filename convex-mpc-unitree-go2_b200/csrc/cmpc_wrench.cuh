@@ -61,6 +61,7 @@ struct Bat {
     int32_t *status, *iters;
     double dt;
     int N, W;
+    const double* cst = nullptr;     // (B,12) cy, sy, 1/m, Iinv[9] formed ahead of the sweeps (robot_consts_kernel), or null
 };
 
 // CTA-wide tables (shared memory): indices depend on the thread, so they must not sit in the constant bank
@@ -324,7 +325,13 @@ CMPC_HD int init_robot(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, int 
     WR_Q_BEGIN
     (void)t; (void)q;
     if (valid) {
-        if (q == 0) robot_consts(e, sh->cst);
+        if (e.bt->cst) {             // formed ahead of the sweeps, all robots at once (no sincos / serial loads in this kernel)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sh->cst[3 * q + c] = e.bt->cst[(size_t)e.b * 12 + 3 * q + c];
+        }
+#if !defined(__CUDA_ARCH__)
+        else if (q == 0) robot_consts(e, sh->cst);      // host emulation: formed here
+#endif
         const double* yo = out_y(e);
         for (int k = 0; k < N; ++k) {
             const int st = stance_at(e, q, k);
@@ -739,7 +746,8 @@ CMPC_HD int forward_sweep(int qlane, bool valid, TS* ts, Sh* sh, const Env& e, c
             uo[0] = fo[0]; uo[1] = fo[1]; uo[2] = fo[2];
             if (code != SWING) yo[12 * k + 3 * q + 2] = -l5[0];
             double* yf = yo + 12 * N + 16 * k + 4 * q;
-            yf[0] = l5[1]; yf[1] = l5[2]; yf[2] = l5[3]; yf[3] = l5[4];
+            { D2 a, b2; a.x = l5[1]; a.y = l5[2]; b2.x = l5[3]; b2.y = l5[4];          // 32-byte aligned: two 16-byte stores
+              reinterpret_cast<D2*>(yf)[0] = a; reinterpret_cast<D2*>(yf)[1] = b2; }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -1088,7 +1096,10 @@ __device__ inline int certify_group(int gl, unsigned gmask, const Params& p, con
     const uint64_t* mk = bt.mask ? bt.mask + (size_t)b * bt.W : nullptr;
     // constants of the robot (every lane; the loads are broadcasts)
     double cst[12];
-    {
+    if (bt.cst) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) cst[i] = bt.cst[(size_t)b * 12 + i];
+    } else {
         double sum = 0.0;
         for (int k = gl; k < N; k += 16) sum += xr[(size_t)5 * N + k];
         const double yaw = grp_sum(sum, gmask) / (double)N;
