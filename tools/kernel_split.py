@@ -1,3 +1,6 @@
+"""Live split of one cmpc_solve call at the bench's size into its kernels (cmpc_set_profile / cmpc_last_kernel_ms3): per solve
+(sweep kernel incl. robot constants, certificate kernel, what is left of the condensed kernel after the join, whole call) in ms.
+Development aid: python tools/kernel_split.py"""
 import sys, os, ctypes
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
