@@ -418,7 +418,8 @@ class CentroidalMPC:
             self._settle_pending()          # stacked vectors of the previous solution somebody still holds are built now
             stream = torch.cuda.current_stream().cuda_stream
             t, use_ab = self._gather(traj, B, stream)
-            torch.cuda.current_stream().synchronize()
+            # (no synchronisation here: the solve is enqueued behind the contact-table kernel on the same stream; update_time
+            # is the host time of the update, as the reference's is, centroidal_mpc.py:73-96)
             t1 = time.perf_counter()
             p = lambda k: t[k].data_ptr() if k in t else None
             self._ev[0].record()
@@ -443,7 +444,9 @@ class CentroidalMPC:
         mk = self._stacked(B, N, sq)
         sol["x"], sol["lam_x"], sol["lam_a"] = (_DM(mk[k], batched) for k in ("x", "lam_x", "lam_a"))
         self._pending = [weakref.ref(sol[k]) for k in ("x", "lam_x", "lam_a")]
-        sol["cost"] = _DM(sq(self._stats[:, 2:3].clone()), batched)
+        stats_ = self._stats
+        sol["cost"] = _DM(lambda: sq(stats_[:B, 2:3].clone()), batched)
+        self._pending.append(weakref.ref(sol["cost"]))
         sol["u"] = sq(self._u.view(B, N, 12).transpose(1, 2))       # (B,12,N): U_opt of test_MPC.py:192
         sol["X"] = sq(self._X.view(B, N, 12).transpose(1, 2))
         sol["status"] = sq(self._status)
