@@ -386,6 +386,15 @@ __global__ void robot_consts_kernel(int B, int N, const double* __restrict__ x_r
     for (int i = 0; i < 9; ++i) o[3 + i] = dc.Iinv[i];
 }
 
+// U_opt[:, 0] of every robot into a compact (B,12) buffer (cmpc_cycle_host, first_step_only): a strided device-to-host copy of
+// 96-byte rows is far slower than this kernel plus one contiguous copy.
+__global__ void first_step_kernel(int B, int N, const double* __restrict__ u, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 12 * B) return;
+    const int b = e / 12, c = e - 12 * b;
+    out[e] = u[(size_t)b * 12 * N + c];
+}
+
 // A head start for the condensed kernel (see cmpc_solve): one thread that lets `cycles` clock ticks pass.
 __global__ void head_start_kernel(long long cycles) {
     const long long t0 = clock64();
@@ -599,7 +608,7 @@ struct cmpc_handle {
         uint64_t* mask = nullptr;
         double *u = nullptr, *y = nullptr, *rho = nullptr, *stats = nullptr;
         int32_t *status = nullptr, *iters = nullptr;
-        double *R_wb = nullptr, *lever = nullptr, *cmd = nullptr, *pos_des = nullptr;      // cmpc_cycle_host only
+        double *R_wb = nullptr, *lever = nullptr, *cmd = nullptr, *pos_des = nullptr, *u0 = nullptr;      // cmpc_cycle_host only
         cudaStream_t s[2] = {nullptr, nullptr};
     } hp;
 };
@@ -778,7 +787,7 @@ int cmpc_destroy(cmpc_handle* h) {
     free_slots(h);
     auto& q = h->hp;
     void* ptrs[] = {q.x0, q.x_ref, q.r_foot, q.I_world, q.mass, q.t0, q.mask, q.u, q.y, q.rho, q.stats, q.status, q.iters,
-                    q.R_wb, q.lever, q.cmd, q.pos_des};
+                    q.R_wb, q.lever, q.cmd, q.pos_des, q.u0};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto s : q.s) if (s) cudaStreamDestroy(s);
     for (auto e : h->pev) if (e) cudaEventDestroy(e);
@@ -1204,6 +1213,7 @@ static int host_path_ready(cmpc_handle* h) {
         CU_TRY(cudaMalloc(&q.lever, mb * 12 * sizeof(double)));
         CU_TRY(cudaMalloc(&q.cmd, mb * 4 * sizeof(double)));
         CU_TRY(cudaMalloc(&q.pos_des, mb * 3 * sizeof(double)));
+        CU_TRY(cudaMalloc(&q.u0, mb * 12 * sizeof(double)));
         q.ready = true;
     }
     return 0;
@@ -1309,9 +1319,11 @@ int cmpc_cycle_host(cmpc_handle* h, int B, const double* x0, const double* R_wor
                        q.I_world + o * 9, q.mass + o, dt, q.mask + o * h->W, warm, q.u + o * 12 * N, q.y + o * 28 * N,
                        q.rho + o, nullptr, nullptr, q.status + o, q.iters + o, q.stats + o * CMPC_NSTAT, s)) { rc = -1; break; }
         cudaError_t e;
-        if (first_step_only)       // U_opt[:, 0], the only column the consumer applies (test_MPC.py:196)
-            e = cudaMemcpy2DAsync(u + o * 12, 12 * sizeof(double), q.u + o * 12 * N, (size_t)12 * N * sizeof(double),
-                                  12 * sizeof(double), (size_t)nb, cudaMemcpyDeviceToHost, s);
+        if (first_step_only) {     // U_opt[:, 0], the only column the consumer applies (test_MPC.py:196)
+            first_step_kernel<<<(12 * nb + 255) / 256, 256, 0, s>>>(nb, N, q.u + o * 12 * N, q.u0 + o * 12);
+            ++g_launches;
+            e = cudaMemcpyAsync(u + o * 12, q.u0 + o * 12, (size_t)nb * 12 * sizeof(double), cudaMemcpyDeviceToHost, s);
+        }
         else
             e = cudaMemcpyAsync(u + o * 12 * N, q.u + o * 12 * N, (size_t)nb * 12 * N * sizeof(double), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(pos_des + o * 3, q.pos_des + o * 3, (size_t)nb * 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
